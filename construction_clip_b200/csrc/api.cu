@@ -1,0 +1,107 @@
+// Context, error reporting and tensor-map construction for libb200clip.
+#include <cstring>
+
+#include "internal.h"
+
+namespace b200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int make_tmap_bf16_2d(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1,
+                      uint64_t pitch_elems, uint32_t box0, uint32_t box1) {
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (pitch_elems * 2) % 16 != 0) {
+        set_error("tensor map: pointer %p / pitch %llu elements not 16-byte aligned", ptr,
+                  (unsigned long long)pitch_elems);
+        return B200CLIP_ERR_ARG;
+    }
+    if (box0 * 2 > 128 || box1 > 256 || box0 == 0 || box1 == 0) {
+        set_error("tensor map: bad box %u x %u", box0, box1);
+        return B200CLIP_ERR_ARG;
+    }
+    cuuint64_t gdim[2] = {dim0, dim1};
+    cuuint64_t gstride[1] = {pitch_elems * 2};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): dims %llu x %llu pitch %llu box %u x %u", (int)r,
+                  (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)pitch_elems, box0, box1);
+        return B200CLIP_ERR_CUDA;
+    }
+    return B200CLIP_OK;
+}
+
+int init_gemm(b200clip_ctx* ctx);
+int init_attention(b200clip_ctx* ctx);
+
+}  // namespace b200
+
+extern "C" {
+
+int b200clip_abi_version(void) { return B200CLIP_ABI_VERSION; }
+
+const char* b200clip_last_error(void) { return b200::g_err; }
+
+int b200clip_ctx_create(b200clip_ctx** out, int device) {
+    if (out == nullptr) {
+        b200::set_error("ctx_create: null out");
+        return B200CLIP_ERR_ARG;
+    }
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        b200::set_error("no CUDA device available (%s); libb200clip has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+        (void)cudaGetLastError();
+        return B200CLIP_ERR_DEVICE;
+    }
+    if (device < 0 || device >= count) {
+        b200::set_error("device %d out of range (count %d)", device, count);
+        return B200CLIP_ERR_DEVICE;
+    }
+    cudaDeviceProp prop;
+    B200_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        b200::set_error("device %d is sm_%d%d; libb200clip is built for sm_100a only", device, prop.major, prop.minor);
+        return B200CLIP_ERR_DEVICE;
+    }
+    B200_CHECK_CUDA(cudaSetDevice(device));
+    B200_CHECK_CUDA(cudaFree(0));  // make sure the primary context exists
+    b200clip_ctx* ctx = new b200clip_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+        b200::set_error("cannot resolve cuTensorMapEncodeTiled from the driver");
+        delete ctx;
+        return B200CLIP_ERR_CUDA;
+    }
+    ctx->encode_tiled = reinterpret_cast<PFN_encodeTiled>(fn);
+    int rc = b200::init_gemm(ctx);
+    if (rc == 0) rc = b200::init_attention(ctx);
+    if (rc != 0) {
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return B200CLIP_OK;
+}
+
+int b200clip_ctx_destroy(b200clip_ctx* ctx) {
+    delete ctx;
+    return B200CLIP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,60 @@
+// Host-side internals shared by the translation units of libb200clip.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdarg>
+#include <cstdio>
+
+#include "../../include/b200clip.h"
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct b200clip_ctx {
+    int device;
+    int num_sms;
+    PFN_encodeTiled encode_tiled;
+};
+
+namespace b200 {
+
+void set_error(const char* fmt, ...);
+
+#define B200_CHECK_ARG(cond, ...)              \
+    do {                                       \
+        if (!(cond)) {                         \
+            b200::set_error(__VA_ARGS__);      \
+            return B200CLIP_ERR_ARG;           \
+        }                                      \
+    } while (0)
+
+#define B200_CHECK_CUDA(expr)                                                                  \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            b200::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return B200CLIP_ERR_CUDA;                                                          \
+        }                                                                                      \
+    } while (0)
+
+#define B200_CHECK_CTX(ctx)                                       \
+    do {                                                          \
+        if ((ctx) == nullptr) {                                   \
+            b200::set_error("null context");                      \
+            return B200CLIP_ERR_ARG;                              \
+        }                                                         \
+    } while (0)
+
+#define B200_LAUNCH_CHECK() B200_CHECK_CUDA(cudaGetLastError())
+
+// 2-D bf16 tensor map, 128-byte swizzle.  dim0 = innermost extent (elements), dim1 = rows,
+// pitch in elements; box = (box0 <= 64, box1 <= 256).
+int make_tmap_bf16_2d(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1,
+                      uint64_t pitch_elems, uint32_t box0, uint32_t box1);
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace b200

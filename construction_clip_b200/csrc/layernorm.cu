@@ -1,0 +1,284 @@
+// LayerNorm forward / backward (HBM-bound): one warp per row, whole row held in registers,
+// fp32 two-pass statistics, bf16 I/O.  Replaces clip.model.LayerNorm (ln_pre, ln_1, ln_2,
+// ln_post, ln_final): upstream casts to fp32, runs nn.LayerNorm(eps=1e-5) and casts back.
+// The forward optionally gathers source rows (CLS / EOT pooling: ln_post(x[:,0,:]),
+// ln_final(x)[arange, argmax]) and fuses the vision token assembly
+// (cat(class_embedding, conv1 output) + positional_embedding) in front of ln_pre.
+#include "common.cuh"
+#include "internal.h"
+
+namespace b200 {
+
+constexpr int kLnThreads = 256;  // 8 rows per block
+
+template <int NV>  // NV = uint4 vectors (8 bf16) per lane, covers d <= NV*256
+__global__ void __launch_bounds__(kLnThreads)
+layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int32_t* __restrict__ row_index,
+                     const __nv_bfloat16* __restrict__ add, int add_period, const __nv_bfloat16* __restrict__ gamma,
+                     const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, int64_t ldy,
+                     __nv_bfloat16* __restrict__ pre_out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                     int rows, int d, float eps) {
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = kLnThreads / 32;
+    const int nvec = d >> 3;
+    for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+        const int64_t src = row_index ? row_index[r] : r;
+        float v[NV][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int vec = lane + 32 * i;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
+            if (vec < nvec) {
+                if (src >= 0) {
+                    const uint4 u = *reinterpret_cast<const uint4*>(x + src * ldx + vec * 8);
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack_bf16(w[j]);
+                        v[i][2 * j] = f.x;
+                        v[i][2 * j + 1] = f.y;
+                    }
+                }
+                if (add != nullptr) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(add + static_cast<int64_t>(r % add_period) * d + vec * 8));
+                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack_bf16(w[j]);
+                        v[i][2 * j] += f.x;
+                        v[i][2 * j + 1] += f.y;
+                    }
+                }
+                if (pre_out != nullptr) {
+                    uint4 o;
+                    o.x = pack_bf16(v[i][0], v[i][1]);
+                    o.y = pack_bf16(v[i][2], v[i][3]);
+                    o.z = pack_bf16(v[i][4], v[i][5]);
+                    o.w = pack_bf16(v[i][6], v[i][7]);
+                    *reinterpret_cast<uint4*>(pre_out + static_cast<int64_t>(r) * ldy + vec * 8) = o;
+                    // statistics are taken on the stored (bf16-rounded) value so that the
+                    // backward, which re-reads pre_out, sees exactly the same x
+                    const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack_bf16(w[j]);
+                        v[i][2 * j] = f.x;
+                        v[i][2 * j + 1] = f.y;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sum += v[i][j];
+            }
+        }
+        const float mean = warp_sum(sum) / d;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (lane + 32 * i < nvec) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float c = v[i][j] - mean;
+                    sq += c * c;
+                }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(sq) / d + eps);
+        if (lane == 0) {
+            if (mean_out) mean_out[r] = mean;
+            if (rstd_out) rstd_out[r] = rstd;
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int vec = lane + 32 * i;
+            if (vec < nvec) {
+                const uint4 g = __ldg(reinterpret_cast<const uint4*>(gamma + vec * 8));
+                const uint4 b = __ldg(reinterpret_cast<const uint4*>(beta + vec * 8));
+                const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
+                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+                uint32_t ow[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 gf = unpack_bf16(gw[j]);
+                    const float2 bf = unpack_bf16(bw[j]);
+                    ow[j] = pack_bf16((v[i][2 * j] - mean) * rstd * gf.x + bf.x,
+                                      (v[i][2 * j + 1] - mean) * rstd * gf.y + bf.y);
+                }
+                *reinterpret_cast<uint4*>(y + static_cast<int64_t>(r) * ldy + vec * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            }
+        }
+    }
+}
+
+// dx = dres + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma,  xhat = (x-mean)*rstd
+template <int NV>
+__global__ void __launch_bounds__(kLnThreads)
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ x,
+                     int64_t ldx, const int32_t* __restrict__ row_index, const __nv_bfloat16* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                     const __nv_bfloat16* __restrict__ dres, int64_t lddres, __nv_bfloat16* __restrict__ dx,
+                     int64_t lddx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int d) {
+    extern __shared__ float s_acc[];  // [2][d]
+    const int lane = threadIdx.x & 31;
+    const int warps_per_block = kLnThreads / 32;
+    const int nvec = d >> 3;
+    for (int i = threadIdx.x; i < 2 * d; i += kLnThreads) s_acc[i] = 0.f;
+    __syncthreads();
+
+    float ag[NV][8], ab[NV][8];
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
+    for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+        const int64_t src = row_index ? row_index[r] : r;
+        const float mu = mean[r], rs = rstd[r];
+        float xh[NV][8], g[NV][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int vec = lane + 32 * i;
+            if (vec < nvec) {
+                const uint4 ux = *reinterpret_cast<const uint4*>(x + src * ldx + vec * 8);
+                const uint4 ud = *reinterpret_cast<const uint4*>(dy + static_cast<int64_t>(r) * lddy + vec * 8);
+                const uint4 ug = __ldg(reinterpret_cast<const uint4*>(gamma + vec * 8));
+                const uint32_t xw[4] = {ux.x, ux.y, ux.z, ux.w};
+                const uint32_t dw[4] = {ud.x, ud.y, ud.z, ud.w};
+                const uint32_t gw[4] = {ug.x, ug.y, ug.z, ug.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float2 xf = unpack_bf16(xw[j]);
+                    const float2 df = unpack_bf16(dw[j]);
+                    const float2 gf = unpack_bf16(gw[j]);
+                    xh[i][2 * j] = (xf.x - mu) * rs;
+                    xh[i][2 * j + 1] = (xf.y - mu) * rs;
+                    ab[i][2 * j] += df.x;
+                    ab[i][2 * j + 1] += df.y;
+                    ag[i][2 * j] += df.x * xh[i][2 * j];
+                    ag[i][2 * j + 1] += df.y * xh[i][2 * j + 1];
+                    g[i][2 * j] = df.x * gf.x;
+                    g[i][2 * j + 1] = df.y * gf.y;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    s1 += g[i][j];
+                    s2 += g[i][j] * xh[i][j];
+                }
+            }
+        }
+        s1 = warp_sum(s1) / d;
+        s2 = warp_sum(s2) / d;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int vec = lane + 32 * i;
+            if (vec < nvec) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
+                if (dres != nullptr) {
+                    const uint4 ur = *reinterpret_cast<const uint4*>(dres + static_cast<int64_t>(r) * lddres + vec * 8);
+                    const uint32_t rw[4] = {ur.x, ur.y, ur.z, ur.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack_bf16(rw[j]);
+                        o[2 * j] += f.x;
+                        o[2 * j + 1] += f.y;
+                    }
+                }
+                uint4 ov;
+                ov.x = pack_bf16(o[0], o[1]);
+                ov.y = pack_bf16(o[2], o[3]);
+                ov.z = pack_bf16(o[4], o[5]);
+                ov.w = pack_bf16(o[6], o[7]);
+                *reinterpret_cast<uint4*>(dx + src * lddx + vec * 8) = ov;
+            }
+        }
+    }
+    if (dgamma != nullptr) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int vec = lane + 32 * i;
+            if (vec < nvec) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    atomicAdd(&s_acc[vec * 8 + j], ag[i][j]);
+                    atomicAdd(&s_acc[d + vec * 8 + j], ab[i][j]);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < d; i += kLnThreads) {
+            atomicAdd(&dgamma[i], s_acc[i]);
+            atomicAdd(&dbeta[i], s_acc[d + i]);
+        }
+    }
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+#define LN_DISPATCH(d, CALL)                       \
+    do {                                           \
+        if ((d) <= 256) { CALL(1); }               \
+        else if ((d) <= 512) { CALL(2); }          \
+        else if ((d) <= 768) { CALL(3); }          \
+        else if ((d) <= 1024) { CALL(4); }         \
+        else if ((d) <= 1536) { CALL(6); }         \
+        else { CALL(8); }                          \
+    } while (0)
+
+extern "C" int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t ldx, const int32_t* row_index,
+                                      const void* add, int64_t add_period, const void* gamma, const void* beta,
+                                      void* y, int64_t ldy, void* pre_out, float* mean, float* rstd, int64_t rows,
+                                      int64_t d, float eps, void* stream) {
+    B200_CHECK_CTX(ctx);
+    B200_CHECK_ARG(x && gamma && beta && y, "layernorm_fwd: null pointer");
+    B200_CHECK_ARG(rows > 0 && rows < (1ll << 31), "layernorm_fwd: bad rows %lld", (long long)rows);
+    B200_CHECK_ARG(d >= 8 && d <= 2048 && d % 8 == 0, "layernorm_fwd: d=%lld must be a multiple of 8 in [8,2048]",
+                   (long long)d);
+    B200_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0, "layernorm_fwd: row pitches must be multiples of 8");
+    B200_CHECK_ARG(add == nullptr || add_period > 0, "layernorm_fwd: add_period must be > 0");
+    const int wpb = kLnThreads / 32;
+    const int64_t want = ceil_div(rows, wpb);
+    const int grid = static_cast<int>(want < ctx->num_sms * 8 ? want : ctx->num_sms * 8);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL(NV)                                                                                                   \
+    layernorm_fwd_kernel<NV><<<grid, kLnThreads, 0, st>>>(                                                         \
+        static_cast<const __nv_bfloat16*>(x), ldx, row_index, static_cast<const __nv_bfloat16*>(add),             \
+        static_cast<int>(add ? add_period : 1), static_cast<const __nv_bfloat16*>(gamma),                         \
+        static_cast<const __nv_bfloat16*>(beta), static_cast<__nv_bfloat16*>(y), ldy,                              \
+        static_cast<__nv_bfloat16*>(pre_out), mean, rstd, static_cast<int>(rows), static_cast<int>(d), eps)
+    LN_DISPATCH(d, CALL);
+#undef CALL
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t lddy, const void* x, int64_t ldx,
+                                      const int32_t* row_index, const void* gamma, const float* mean,
+                                      const float* rstd, const void* dres, int64_t lddres, void* dx, int64_t lddx,
+                                      float* dgamma, float* dbeta, int64_t rows, int64_t d, void* stream) {
+    B200_CHECK_CTX(ctx);
+    B200_CHECK_ARG(dy && x && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
+    B200_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must come together");
+    B200_CHECK_ARG(rows > 0 && rows < (1ll << 31), "layernorm_bwd: bad rows");
+    B200_CHECK_ARG(d >= 8 && d <= 2048 && d % 8 == 0, "layernorm_bwd: bad d=%lld", (long long)d);
+    B200_CHECK_ARG(lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && (dres == nullptr || lddres % 8 == 0),
+                   "layernorm_bwd: row pitches must be multiples of 8");
+    const int wpb = kLnThreads / 32;
+    const int64_t want = ceil_div(rows, wpb * 4);  // >= 4 rows per warp amortise the dgamma/dbeta atomics
+    const int grid = static_cast<int>(want < ctx->num_sms * 4 ? (want > 0 ? want : 1) : ctx->num_sms * 4);
+    const size_t smem = 2 * d * sizeof(float);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define CALL(NV)                                                                                                    \
+    layernorm_bwd_kernel<NV><<<grid, kLnThreads, smem, st>>>(                                                       \
+        static_cast<const __nv_bfloat16*>(dy), lddy, static_cast<const __nv_bfloat16*>(x), ldx, row_index,         \
+        static_cast<const __nv_bfloat16*>(gamma), mean, rstd, static_cast<const __nv_bfloat16*>(dres), lddres,     \
+        static_cast<__nv_bfloat16*>(dx), lddx, dgamma, dbeta, static_cast<int>(rows), static_cast<int>(d))
+    LN_DISPATCH(d, CALL);
+#undef CALL
+    B200_LAUNCH_CHECK();
+    return 0;
+}

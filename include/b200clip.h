@@ -1,0 +1,196 @@
+/*
+ * libb200clip -- C ABI of the B200 (sm_100a) CLIP dual-encoder hot path.
+ *
+ * The reference (zhuluntsai/Construction-CLIP) has no FFI/plugin layer: its hot path
+ * sits behind the Python API of the third-party `clip` package
+ *   clip.load                CLIP/predict.py:12, CLIP/train.py:105, CLIP_prefix_caption/parse_coco.py:20
+ *   model(image, text)       CLIP/predict.py:46, CLIP/train.py:161, parse_coco.py:45,50
+ *   model.encode_image       parse_coco.py:43, application.py:97
+ *   CE(lpi)+CE(lpt) / 2      CLIP/train.py:162-166
+ *   loss.backward()          CLIP/train.py:168
+ * and, below that, behind torch operators (nn.Conv2d, nn.LayerNorm, nn.MultiheadAttention,
+ * nn.Linear, QuickGELU, matmul, CrossEntropyLoss).  Each entry point below replaces one
+ * such operator (or a fused group of them); the comment on each names what it replaces.
+ * The Python package `clip/` shipped with this repository binds them through ctypes
+ * (see INTEGRATION.md).
+ *
+ * Conventions
+ *  - every function returns 0 on success, a negative B200CLIP_ERR_* otherwise;
+ *    b200clip_last_error() returns a thread-local message for the last failure.
+ *  - all data pointers are DEVICE pointers owned by the caller; the library never frees
+ *    or retains them.  `stream` is a cudaStream_t passed as void*.
+ *  - bf16 = __nv_bfloat16 storage; "rows x cols, ld" = row-major with a row pitch of `ld`
+ *    elements.  Row pitches of bf16 matrices fed to the tensor-core GEMM must be multiples
+ *    of 8 elements (16 bytes, a TMA requirement) and base pointers 16-byte aligned.
+ *  - no function synchronises the device or allocates memory after ctx creation, so all of
+ *    them can be captured into a CUDA graph.
+ *  - there is no CPU fallback: without an sm_100 device every call fails with
+ *    B200CLIP_ERR_DEVICE.
+ */
+#ifndef B200CLIP_H
+#define B200CLIP_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200CLIP_ABI_VERSION 1
+
+enum {
+    B200CLIP_OK = 0,
+    B200CLIP_ERR_ARG = -1,     /* bad argument (shape, alignment, enum) */
+    B200CLIP_ERR_DEVICE = -2,  /* no sm_100 device / wrong device */
+    B200CLIP_ERR_CUDA = -3,    /* a CUDA runtime / driver call failed */
+    B200CLIP_ERR_UNSUPPORTED = -4
+};
+
+/* operand storage order for the tensor-core GEMM */
+enum {
+    B200CLIP_MAJOR_K = 0,  /* operand stored [rows(M or N), K], K contiguous  */
+    B200CLIP_MAJOR_MN = 1  /* operand stored [K, rows(M or N)], M/N contiguous */
+};
+
+/* GEMM epilogues */
+enum {
+    B200CLIP_EPI_NONE = 0,          /* C = acc (+bias)                                      */
+    B200CLIP_EPI_QUICKGELU = 1,     /* C = quickgelu(acc+bias); optional preact = acc+bias  */
+    B200CLIP_EPI_RESIDUAL = 2,      /* C = acc + bias + aux                                 */
+    B200CLIP_EPI_QUICKGELU_BWD = 3  /* C = acc * quickgelu'(aux)                            */
+};
+
+enum { B200CLIP_DT_BF16 = 0, B200CLIP_DT_F32 = 1 };
+
+typedef struct b200clip_ctx b200clip_ctx;
+
+int b200clip_abi_version(void);
+const char* b200clip_last_error(void);
+/* Creates the per-device context (resolves the driver's tensor-map encoder, sets kernel
+ * attributes).  Fails with B200CLIP_ERR_DEVICE when `device` is not compute capability 10.x. */
+int b200clip_ctx_create(b200clip_ctx** out, int device);
+int b200clip_ctx_destroy(b200clip_ctx* ctx);
+
+/* ---- nn.Linear / F.linear (+ fused epilogue); its dgrad and wgrad -------------------------
+ * C[M,N] = sum_k A(m,k) * B(n,k)  (+ bias[n]) -> epilogue.          tcgen05 / TMEM / TMA.
+ *   forward  y = x W^T + b : A = x [M,K] K-major,  B = W [N,K] K-major
+ *   dgrad    dx = dy W     : A = dy [M,N'] K-major, B = W [N',K'] as MN-major (N := K', K := N')
+ *   wgrad    dW = dy^T x   : A = dy [T,N'] MN-major (M := N'), B = x [T,K'] MN-major (N := K'), K := T
+ * a_major/b_major: B200CLIP_MAJOR_*.  lda/ldb: row pitch (elements) of the STORED matrix.
+ * out_dtype: B200CLIP_DT_BF16 or _F32.  bias: bf16 [N] or NULL.  aux: bf16 [M,N] (ldaux) or NULL.
+ * preact: bf16 [M,N] (ldc pitch) or NULL (EPI_QUICKGELU only).
+ * scale: optional device fp32 scalar; acc is multiplied by it before bias (NULL = 1).
+ * split_k > 1 splits the reduction over `split_k` CTAs per tile and ACCUMULATES into C with
+ * fp32 atomics (requires out_dtype F32, EPI_NONE, no bias; C must be pre-zeroed or hold a
+ * value to accumulate onto).  split_k = 0 lets the library choose (only when out is F32).
+ * accumulate != 0 with out F32 adds to C instead of overwriting (atomic). */
+int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda, int a_major, const void* B, int64_t ldb,
+                       int b_major, void* C, int64_t ldc, int out_dtype, const void* bias, const void* aux,
+                       int64_t ldaux, void* preact, const float* scale, int64_t M, int64_t N, int64_t K,
+                       int epilogue, int split_k, int accumulate, void* stream);
+
+/* ---- clip.model.LayerNorm (fp32 statistics, eps, affine) ------------------------------------
+ * y[r,:] = LN(x[src(r),:]) * gamma + beta ; src(r) = row_index ? row_index[r] : r.
+ * Optional fused add before normalisation (vision token assembly, replaces
+ * cat(class_embedding, conv) + positional_embedding + ln_pre):
+ *   v = x[src(r),:] + add[(r % add_period),:]   when add != NULL.
+ * If pre_out != NULL the pre-normalisation value v is also stored (bf16, ldy pitch).
+ * mean/rstd: fp32 [rows] or NULL. */
+int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t ldx, const int32_t* row_index, const void* add,
+                           int64_t add_period, const void* gamma, const void* beta, void* y, int64_t ldy,
+                           void* pre_out, float* mean, float* rstd, int64_t rows, int64_t d, float eps, void* stream);
+/* dx[dst(r),:] = (dres ? dres[r,:] : 0) + LN'(dy[r,:]) ; dgamma/dbeta fp32 [d] ACCUMULATED (atomics).
+ * x is read with the same src(r) mapping as the forward; dx is written at dst(r) = src(r). */
+int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t lddy, const void* x, int64_t ldx,
+                           const int32_t* row_index, const void* gamma, const float* mean, const float* rstd,
+                           const void* dres, int64_t lddres, void* dx, int64_t lddx, float* dgamma, float* dbeta,
+                           int64_t rows, int64_t d, void* stream);
+
+/* ---- nn.MultiheadAttention(need_weights=False) core: softmax(q k^T / 8 + mask) v, head_dim 64 ----
+ * qkv: bf16 [B*S, 3*H*64] (the packed in_proj output: q | k | v, each head-major), out: bf16 [B*S, H*64].
+ * causal != 0 applies upstream's build_attention_mask (-inf strictly above the diagonal; padding is
+ * NOT masked).  S <= 128 (single tile) in this version. */
+int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, int64_t B, int64_t S, int64_t H, int causal,
+                      void* stream);
+/* dqkv: bf16 [B*S, 3*H*64]; probabilities are recomputed from qkv (nothing saved by the forward). */
+int b200clip_attn_bwd(b200clip_ctx* ctx, const void* qkv, const void* dout, void* dqkv, int64_t B, int64_t S,
+                      int64_t H, int causal, void* stream);
+
+/* ---- token_embedding(text) + positional_embedding  (clip.model.CLIP.encode_text) ---------------
+ * ids int32 [B,S]; table bf16 [V,d]; pos bf16 [S,d]; out bf16 [B*S,d]; eot_row int32 [B] receives
+ * b*S + argmax_s ids[b,s] (first maximum) -- the row upstream pools at. */
+int b200clip_embed_tokens_fwd(b200clip_ctx* ctx, const int32_t* ids, const void* table, const void* pos, void* out,
+                              int32_t* eot_row, int64_t B, int64_t S, int64_t d, int64_t vocab, void* stream);
+/* dtable fp32 [V,d] and dpos fp32 [S,d] are ACCUMULATED into (atomics). */
+int b200clip_embed_tokens_bwd(b200clip_ctx* ctx, const int32_t* ids, const void* dout, float* dtable, float* dpos,
+                              int64_t B, int64_t S, int64_t d, int64_t vocab, void* stream);
+
+/* ---- visual.conv1 (Conv2d, kernel = stride = patch, no bias) as im2col + GEMM ---------------------
+ * image: [B,3,R,R] bf16 or fp32 (in_dtype) -> cols bf16 [B*g*g, ldcols], ldcols >= 3*p*p (padded
+ * columns are zero-filled); column order (c, py, px) matches conv1.weight.view(width, 3*p*p). */
+int b200clip_im2col_patch(b200clip_ctx* ctx, const void* image, int in_dtype, void* cols, int64_t ldcols, int64_t B,
+                          int64_t R, int64_t patch, void* stream);
+
+/* ---- small fused helpers ---------------------------------------------------------------------- */
+/* colsum: out[n] (+)= sum_m x[m,n]; x bf16 [M,N] (ldx); out fp32 [N] accumulated (bias gradients). */
+int b200clip_colsum(b200clip_ctx* ctx, const void* x, int64_t ldx, float* out, int64_t M, int64_t N, void* stream);
+/* vision token-assembly backward: dpre bf16 [B*n, d] -> dpatch bf16 [B*(n-1), d] (rows 1..n-1 of each
+ * sample), dpos fp32 [n,d] += sum_b dpre[b,t,:], dcls fp32 [d] += sum_b dpre[b,0,:]. */
+int b200clip_vision_assemble_bwd(b200clip_ctx* ctx, const void* dpre, void* dpatch, float* dpos, float* dcls,
+                                 int64_t B, int64_t n, int64_t d, void* stream);
+/* y = x / ||x||_2 per row; x fp32 [B,E] -> y fp32 [B,E], inv_norm fp32 [B]. */
+int b200clip_l2norm_fwd(b200clip_ctx* ctx, const float* x, float* y, float* inv_norm, int64_t B, int64_t E,
+                        void* stream);
+/* dx = (dy - y * <y,dy>) * inv_norm, output bf16 (feeds the projection dgrad/wgrad GEMMs). */
+int b200clip_l2norm_bwd(b200clip_ctx* ctx, const float* dy, const float* y, const float* inv_norm, void* dx_bf16,
+                        int64_t B, int64_t E, void* stream);
+/* dtype conversion of flat buffers (n elements) */
+int b200clip_cast_f32_to_bf16(b200clip_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
+int b200clip_cast_bf16_to_f32(b200clip_ctx* ctx, const void* src, float* dst, int64_t n, void* stream);
+
+/* ---- logit_scale.exp() * I @ T.t()  (CLIP.forward) ---------------------------------------------
+ * img fp32 [Bi,E] and txt fp32 [Bt,E] are the L2-normalised features; logit_scale is the device
+ * scalar parameter (the kernel applies exp).  logits fp32 [Bi,Bt] (= logits_per_image). */
+int b200clip_logits(b200clip_ctx* ctx, const float* img, const float* txt, const float* logit_scale, float* logits,
+                    int64_t Bi, int64_t Bt, int64_t E, void* stream);
+
+/* Scratch bytes the two loss entry points below need (caller-allocated device memory, contents
+ * are not preserved between calls); -1 on bad arguments. */
+int64_t b200clip_clip_loss_workspace_bytes(b200clip_ctx* ctx, int64_t Bl, int64_t Bg, int64_t E);
+
+/* ---- fused similarity + symmetric softmax cross-entropy (CLIP/train.py:162-166) -----------------
+ * Local-rows formulation for data parallelism: this rank owns rows [row0, row0+Bl) of the global
+ * batch Bg.  img_all / txt_all fp32 [Bg,E] are the (all-gathered) normalised features.
+ * Forward: for the local rows i computes  lse_i[i] = logsumexp_j s*<img_i,txt_j>,
+ * lse_t[i] = logsumexp_j s*<txt_i,img_j>, diag, and
+ *   loss_sum[0] += sum_i (lse_i[i] - diag_i) ; loss_sum[1] += sum_i (lse_t[i] - diag_i),
+ *   correct[0] += #{i : argmax_j logits_per_image[i,j] == i}   (CLIP/train.py:173)
+ * without ever writing the Bg x Bg logits.  The global loss is (loss_sum[0]+loss_sum[1])/(2*Bg),
+ * summed over ranks.  lse_i, lse_t: fp32 [Bl]. */
+int b200clip_clip_loss_fwd(b200clip_ctx* ctx, const float* img_all, const float* txt_all, const float* logit_scale,
+                           int64_t row0, int64_t Bl, int64_t Bg, int64_t E, float* lse_i, float* lse_t,
+                           float* loss_sum, int32_t* correct, void* workspace, int64_t workspace_bytes,
+                           void* stream);
+/* Backward for the local rows given the GLOBAL row-LSE vectors lse_i_all / lse_t_all fp32 [Bg]
+ * (all-gathered; identical to the local ones when Bl == Bg):
+ *   d_img[i] = g*s/(2Bg) * sum_j (p_img[i,j] + p_txt[j,i] - 2*delta_ij) txt_j      (fp32 [Bl,E])
+ *   d_txt[i] = g*s/(2Bg) * sum_j (p_txt[i,j] + p_img[j,i] - 2*delta_ij) img_j
+ *   d_logit_scale[0] += the local rows' share of dL/dlogit_scale
+ * where p_img[i,j] = exp(s<img_i,txt_j> - lse_i[i]), p_txt[i,j] = exp(s<txt_i,img_j> - lse_t[i]),
+ * g = *grad_out (device scalar, NULL = 1).  Exact gradients for this rank's slice, no gradient
+ * collective needed. */
+int b200clip_clip_loss_bwd(b200clip_ctx* ctx, const float* img_all, const float* txt_all, const float* logit_scale,
+                           const float* lse_i_all, const float* lse_t_all, const float* grad_out, int64_t row0,
+                           int64_t Bl, int64_t Bg, int64_t E, float* d_img, float* d_txt, float* d_logit_scale,
+                           void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---- AdamW step (CLIP/train.py:143,169) on flat buffers: fp32 master weights, bf16 shadow -------
+ * p -= lr * (m_hat / (sqrt(v_hat) + eps) + wd * p);  grad fp32 (multiplied by grad_scale). */
+int b200clip_adamw(b200clip_ctx* ctx, float* master, void* param_bf16, const float* grad, float* m, float* v,
+                   int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                   int64_t step, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200CLIP_H */

@@ -1,0 +1,274 @@
+"""Kernel-level parity tests (GPU): every C-ABI entry point against a plain fp32 PyTorch
+statement of the same operator on the same seeded inputs.  Tolerances are bf16-level:
+inputs are bf16-exact, accumulation is fp32, outputs are rounded to bf16 once."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from construction_clip_b200 import ops as O
+    return O
+
+
+def _rand(shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(shape, device="cuda", generator=g) * scale).to(bf16)
+
+
+def _close(got, ref, atol, rtol, what=""):
+    got, ref = got.float(), ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = err > tol
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} mismatches, max err {err.max().item():.4g} "
+                           f"(ref max {ref.abs().max().item():.4g}); first bad idx {bad.nonzero()[0].tolist()}")
+
+
+GEMM_SHAPES = [
+    (128, 128, 64), (128, 256, 64), (128, 128, 256), (256, 512, 192), (1600, 2304, 768), (1232, 512, 2048),
+    (77, 136, 72), (3000, 768, 3072), (32, 512, 768), (6400, 3072, 768),
+]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_nt(ops, M, N, K):
+    a, b = _rand((M, K), seed=1), _rand((N, K), seed=2)
+    got = ops.gemm(a, b)
+    ref = a.float() @ b.float().t()
+    _close(got, ref, 2e-2 * math.sqrt(K / 64), 1e-2, f"gemm NT {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_nn_dgrad(ops, M, N, K):
+    from construction_clip_b200 import lib as L
+    a, b = _rand((M, K), seed=3), _rand((K, N), seed=4)   # B stored [K, N]  (MN-major)
+    got = ops.gemm(a, b, b_major=L.MAJOR_MN)
+    ref = a.float() @ b.float()
+    _close(got, ref, 2e-2 * math.sqrt(K / 64), 1e-2, f"gemm NN {M}x{N}x{K}")
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (768, 768, 6400), (2304, 768, 1600),
+                                   (512, 2048, 9856), (136, 72, 77 * 8)])
+def test_gemm_tn_wgrad(ops, M, N, K):
+    from construction_clip_b200 import lib as L
+    a, b = _rand((K, M), seed=5), _rand((K, N), seed=6)   # both stored [K, *]  (MN-major)
+    out = torch.zeros((M, N), device="cuda", dtype=f32)
+    ops.gemm(a, b, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, out=out, split_k=0, accumulate=True)
+    ref = a.float().t() @ b.float()
+    _close(out, ref, 1e-3 * math.sqrt(K), 1e-3, f"gemm TN {M}x{N}x{K}")
+    # accumulate semantics: a second call adds on top
+    ops.gemm(a, b, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, out=out, split_k=3, accumulate=True)
+    _close(out, 2 * ref, 2e-3 * math.sqrt(K), 1e-3, f"gemm TN accumulate {M}x{N}x{K}")
+
+
+def test_gemm_epilogues(ops):
+    from construction_clip_b200 import lib as L
+    M, N, K = 1000, 768, 512
+    a, w = _rand((M, K), seed=7), _rand((N, K), 0.05, seed=8)
+    bias, aux = _rand((N,), seed=9), _rand((M, N), seed=10)
+    base = a.float() @ w.float().t() + bias.float()
+    _close(ops.gemm(a, w, bias=bias), base, 3e-2, 1e-2, "bias")
+    pre = torch.empty((M, N), device="cuda", dtype=bf16)
+    got = ops.gemm(a, w, bias=bias, epilogue=L.EPI_QUICKGELU, preact=pre)
+    _close(pre, base, 3e-2, 1e-2, "preact")
+    _close(got, base * torch.sigmoid(1.702 * base), 3e-2, 1e-2, "quickgelu")
+    _close(ops.gemm(a, w, bias=bias, epilogue=L.EPI_RESIDUAL, aux=aux), base + aux.float(), 3e-2, 1e-2, "residual")
+    s = torch.sigmoid(1.702 * aux.float())
+    gref = (a.float() @ w.float().t()) * (s * (1 + 1.702 * aux.float() * (1 - s)))
+    _close(ops.gemm(a, w, epilogue=L.EPI_QUICKGELU_BWD, aux=aux), gref, 3e-2, 1e-2, "quickgelu_bwd")
+    sc = torch.tensor([0.37], device="cuda")
+    _close(ops.gemm(a, w, scale=sc, out_dtype=f32), 0.37 * (a.float() @ w.float().t()), 1e-3, 1e-3, "scale f32")
+    # strided A (row pitch > K): the CLS-row gather pattern x[:, 0, :]
+    big = _rand((64, 5 * K), seed=11)
+    view = big[:, :K]
+    _close(ops.gemm(view, w), view.float() @ w.float().t(), 3e-2, 1e-2, "strided A")
+
+
+@pytest.mark.parametrize("rows,d", [(1600, 768), (1232, 512), (77, 128), (515, 1024)])
+def test_layernorm(ops, rows, d):
+    x = _rand((rows, d), 2.0, seed=1)
+    g = (1 + 0.1 * torch.randn(d, device="cuda")).to(bf16)
+    b = (0.1 * torch.randn(d, device="cuda")).to(bf16)
+    y, mean, rstd = ops.layernorm_fwd(x, g, b, want_stats=True)
+    ref = torch.nn.functional.layer_norm(x.float(), (d,), g.float(), b.float(), 1e-5)
+    _close(y, ref, 2e-2, 1e-2, "ln fwd")
+    _close(mean, x.float().mean(-1), 1e-5, 1e-5, "mean")
+    # backward vs autograd
+    xr = x.float().requires_grad_(True)
+    gr, br = g.float().requires_grad_(True), b.float().requires_grad_(True)
+    dy = _rand((rows, d), seed=2)
+    dres = _rand((rows, d), seed=3)
+    torch.nn.functional.layer_norm(xr, (d,), gr, br, 1e-5).backward(dy.float())
+    dg = torch.zeros(d, device="cuda")
+    db = torch.zeros(d, device="cuda")
+    dx = ops.layernorm_bwd(dy, x, g, mean, rstd, dg, db, dres=dres)
+    _close(dx, xr.grad + dres.float(), 3e-2, 2e-2, "ln dx")
+    _close(dg, gr.grad, 1e-2 * math.sqrt(rows), 1e-2, "ln dgamma")
+    _close(db, br.grad, 1e-2 * math.sqrt(rows), 1e-2, "ln dbeta")
+
+
+def test_layernorm_gather_and_assemble(ops):
+    B, n, d = 6, 50, 768
+    x = _rand((B * n, d), seed=1)
+    g, b = _rand((d,), seed=2), _rand((d,), seed=3)
+    idx = (torch.arange(B, device="cuda", dtype=torch.int32) * n)
+    y = ops.layernorm_fwd(x, g, b, row_index=idx)
+    ref = torch.nn.functional.layer_norm(x.float()[idx.long()], (d,), g.float(), b.float(), 1e-5)
+    _close(y, ref, 2e-2, 1e-2, "ln gather")
+    # vision token assembly: row (b,t): t==0 -> cls+pos[0] ; else patch[b,t-1] + pos[t]
+    patch = _rand((B * (n - 1), d), seed=4)
+    poscls = _rand((n, d), seed=5)
+    ridx = torch.full((B, n), -1, dtype=torch.int32, device="cuda")
+    ridx[:, 1:] = (torch.arange(B, device="cuda")[:, None] * (n - 1) + torch.arange(n - 1, device="cuda")[None]).int()
+    pre = torch.empty((B * n, d), device="cuda", dtype=bf16)
+    y = ops.layernorm_fwd(patch, g, b, rows=B * n, row_index=ridx.reshape(-1).contiguous(), add=poscls, add_period=n,
+                          pre_out=pre)
+    full = torch.cat([torch.zeros(B, 1, d, device="cuda"), patch.float().view(B, n - 1, d)], 1) + poscls.float()
+    _close(pre, full.view(-1, d), 2e-2, 1e-2, "assemble pre")
+    _close(y, torch.nn.functional.layer_norm(pre.float(), (d,), g.float(), b.float(), 1e-5), 2e-2, 1e-2, "assemble ln")
+
+
+def _attn_ref(qkv, B, S, H, causal):
+    d = H * 64
+    q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / 8.0
+    if causal:
+        s = s + torch.full((S, S), float("-inf"), device=qkv.device).triu_(1)
+    o = torch.softmax(s, -1) @ v
+    return o.permute(0, 2, 1, 3).reshape(B * S, d)
+
+
+@pytest.mark.parametrize("B,S,H,causal", [(2, 50, 12, False), (3, 77, 8, True), (1, 64, 2, False), (2, 16, 2, True),
+                                          (1, 128, 2, True), (40, 50, 12, False), (33, 77, 8, True), (2, 7, 1, True)])
+def test_attention_fwd_bwd(ops, B, S, H, causal):
+    qkv = _rand((B * S, 3 * H * 64), 1.5, seed=S)
+    out = ops.attn_fwd(qkv, B, S, H, causal)
+    qr = qkv.float().requires_grad_(True)
+    ref = _attn_ref(qr, B, S, H, causal)
+    _close(out, ref, 2e-2, 2e-2, "attn fwd")
+    dout = _rand((B * S, H * 64), seed=S + 1)
+    ref.backward(dout.float())
+    dqkv = ops.attn_bwd(qkv, dout, B, S, H, causal)
+    _close(dqkv, qr.grad, 4e-2, 4e-2, "attn bwd")
+
+
+def test_embed_tokens(ops):
+    B, S, d, V = 9, 77, 512, 49408
+    g = torch.Generator(device="cuda").manual_seed(0)
+    ids = torch.randint(1, 49406, (B, S), device="cuda", generator=g, dtype=torch.int32)
+    lens = torch.randint(3, 77, (B,), device="cuda", generator=g)
+    for b in range(B):
+        ids[b, 0] = 49406
+        ids[b, int(lens[b])] = 49407
+        ids[b, int(lens[b]) + 1:] = 0
+    table, pos = _rand((V, d), 0.02, seed=1), _rand((S, d), 0.01, seed=2)
+    out, eot = ops.embed_tokens_fwd(ids, table, pos)
+    ref = table.float()[ids.long()] + pos.float()[None]
+    _close(out, ref.view(-1, d), 1e-3, 1e-2, "embed fwd")
+    assert torch.equal(eot.long(), torch.arange(B, device="cuda") * S + ids.long().argmax(-1))
+    dout = _rand((B * S, d), seed=3)
+    dout.view(B, S, d)[0, 40:] = 0
+    dt = torch.zeros((V, d), device="cuda")
+    dp = torch.zeros((S, d), device="cuda")
+    ops.embed_tokens_bwd(ids, dout, dt, dp)
+    rt = torch.zeros((V, d), device="cuda").index_add_(0, ids.long().view(-1), dout.float())
+    _close(dt, rt, 1e-3, 1e-3, "embed dtable")
+    _close(dp, dout.float().view(B, S, d).sum(0), 1e-3, 1e-3, "embed dpos")
+
+
+@pytest.mark.parametrize("R,p,dtype", [(224, 32, f32), (224, 16, bf16), (224, 14, f32), (64, 32, bf16)])
+def test_im2col(ops, R, p, dtype):
+    B = 3
+    img = torch.randn(B, 3, R, R, device="cuda").to(dtype)
+    cols = ops.im2col_patch(img, p)
+    g = R // p
+    ref = img.float().view(B, 3, g, p, g, p).permute(0, 2, 4, 1, 3, 5).reshape(B * g * g, 3 * p * p)
+    k = 3 * p * p
+    _close(cols[:, :k], ref.to(bf16), 0, 0, "im2col")
+    assert (cols[:, k:] == 0).all()
+
+
+def test_colsum_l2norm_cast_assemble_bwd(ops):
+    x = _rand((5000, 768), seed=1)
+    out = torch.zeros(768, device="cuda")
+    ops.colsum(x, out)
+    _close(out, x.float().sum(0), 0.5, 1e-3, "colsum")
+    f = torch.randn(37, 512, device="cuda")
+    y, inv = ops.l2norm_fwd(f)
+    _close(y, f / f.norm(dim=1, keepdim=True), 1e-6, 1e-5, "l2norm")
+    fr = f.clone().requires_grad_(True)
+    dy = torch.randn(37, 512, device="cuda")
+    (fr / fr.norm(dim=1, keepdim=True)).backward(dy)
+    _close(ops.l2norm_bwd(dy, y, inv), fr.grad, 1e-3, 1e-2, "l2norm bwd")
+    src = torch.randn(100003, device="cuda")
+    _close(ops.cast_f32_to_bf16(src[:100000]), src[:100000].to(bf16), 0, 0, "cast")
+    B, n, d = 7, 50, 768
+    dpre = _rand((B * n, d), seed=2)
+    dpos = torch.zeros((n, d), device="cuda")
+    dcls = torch.zeros(d, device="cuda")
+    dpatch = ops.vision_assemble_bwd(dpre, B, n, dpos, dcls)
+    v = dpre.float().view(B, n, d)
+    _close(dpatch, v[:, 1:].reshape(-1, d), 0, 0, "assemble dpatch")
+    _close(dpos, v.sum(0), 1e-3, 1e-3, "assemble dpos")
+    _close(dcls, v[:, 0].sum(0), 1e-3, 1e-3, "assemble dcls")
+
+
+@pytest.mark.parametrize("Bg,E,row0,Bl", [(64, 512, 0, 64), (200, 512, 0, 200), (1024, 512, 256, 128), (96, 768, 32, 64)])
+def test_clip_loss(ops, Bg, E, row0, Bl):
+    torch.manual_seed(Bg)
+    img = torch.nn.functional.normalize(torch.randn(Bg, E, device="cuda"), dim=1)
+    txt = torch.nn.functional.normalize(img * 0.4 + torch.randn(Bg, E, device="cuda") * 0.05, dim=1)
+    ls = torch.tensor([math.log(1 / 0.07)], device="cuda")
+    lg = ops.logits(img, txt, ls)
+    _close(lg, ls.exp() * img @ txt.t(), 1e-4, 1e-5, "logits")
+    ir, tr, lr = img.clone().requires_grad_(True), txt.clone().requires_grad_(True), ls.clone().requires_grad_(True)
+    L_ref = lr.exp() * ir @ tr.t()
+    lab = torch.arange(Bg, device="cuda")
+    loss_ref = (torch.nn.functional.cross_entropy(L_ref, lab) + torch.nn.functional.cross_entropy(L_ref.t(), lab)) / 2
+    loss_ref.backward()
+    ws = ops.clip_loss_workspace(img.device, Bl, Bg, E)
+    # full-batch LSE vectors come from running the forward over every row block (what the
+    # all-gather provides in the multi-GPU path)
+    lse_i_all = torch.empty(Bg, device="cuda")
+    lse_t_all = torch.empty(Bg, device="cuda")
+    tot = torch.zeros(2, device="cuda")
+    correct = 0
+    for r0 in range(0, Bg, Bl):
+        bl = min(Bl, Bg - r0)
+        a, b, s, c = ops.clip_loss_fwd(img, txt, ls, r0, bl, ws)
+        lse_i_all[r0:r0 + bl], lse_t_all[r0:r0 + bl] = a, b
+        tot += s
+        correct += int(c)
+    loss = (tot[0] + tot[1]) / (2 * Bg)
+    assert abs(loss.item() - loss_ref.item()) <= 1e-4 * max(1.0, abs(loss_ref.item())), (loss.item(), loss_ref.item())
+    assert correct == int((L_ref.argmax(1) == lab).sum())
+    d_img, d_txt, d_ls = ops.clip_loss_bwd(img, txt, ls, lse_i_all, lse_t_all, None, row0, Bl, ws)
+    scale = max(ir.grad.abs().max().item(), 1e-6)
+    _close(d_img, ir.grad[row0:row0 + Bl], 2e-2 * scale, 2e-2, "d_img")
+    _close(d_txt, tr.grad[row0:row0 + Bl], 2e-2 * scale, 2e-2, "d_txt")
+    if Bl == Bg:
+        assert abs(d_ls.item() - lr.grad.item()) <= 1e-3 * max(1.0, abs(lr.grad.item())), (d_ls.item(), lr.grad.item())
+
+
+def test_adamw(ops):
+    n = 100000
+    p = torch.randn(n, device="cuda")
+    g = torch.randn(n, device="cuda") * 0.1
+    ref = p.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref], lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
+    master, m, v = p.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    shadow = torch.empty(n, device="cuda", dtype=bf16)
+    for step in range(1, 4):
+        ref.grad = g.clone()
+        opt.step()
+        ops.adamw(master, shadow, g, m, v, lr=1e-3, beta1=0.9, beta2=0.98, eps=1e-6, weight_decay=0.2, grad_scale=1.0,
+                  step=step)
+    _close(master, ref.detach(), 1e-5, 1e-5, "adamw")
+    _close(shadow, master.to(bf16), 0, 0, "adamw shadow")
