@@ -63,10 +63,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 255u) == 0) {
+        if ((++spins & 15u) == 0) {
             uint64_t t1;
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 4000000000ull) {  // 4 s
+            if (t1 - t0 > 2000000000ull) {  // 2 s
                 printf("b200clip: mbarrier watchdog block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
                        smem_u32(bar), parity);
                 __trap();
