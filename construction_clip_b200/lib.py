@@ -49,7 +49,7 @@ SIGNATURES = {
 _RESTYPES = {"b200clip_last_error": C.c_char_p, "b200clip_clip_loss_workspace_bytes": C.c_int64}
 
 _lib = None
-_lock = threading.Lock()
+_lock = threading.RLock()
 _ctx: dict[int, int] = {}
 
 
