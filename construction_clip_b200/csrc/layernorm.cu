@@ -14,8 +14,9 @@ constexpr int kLnThreads = 256;  // 8 rows per block
 template <int NV>  // NV = uint4 vectors (8 bf16) per lane, covers d <= NV*256
 __global__ void __launch_bounds__(kLnThreads)
 layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int32_t* __restrict__ row_index,
-                     const __nv_bfloat16* __restrict__ add, int add_period, const __nv_bfloat16* __restrict__ gamma,
-                     const __nv_bfloat16* __restrict__ beta, __nv_bfloat16* __restrict__ y, int64_t ldy,
+                     const __nv_bfloat16* __restrict__ neg_row, const __nv_bfloat16* __restrict__ add, int add_period,
+                     const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                     __nv_bfloat16* __restrict__ y, int64_t ldy,
                      __nv_bfloat16* __restrict__ pre_out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                      int rows, int d, float eps) {
     const int lane = threadIdx.x & 31;
@@ -31,8 +32,9 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
             if (vec < nvec) {
-                if (src >= 0) {
-                    const uint4 u = *reinterpret_cast<const uint4*>(x + src * ldx + vec * 8);
+                if (src >= 0 || neg_row != nullptr) {
+                    const uint4 u = (src >= 0) ? *reinterpret_cast<const uint4*>(x + src * ldx + vec * 8)
+                                               : __ldg(reinterpret_cast<const uint4*>(neg_row + vec * 8));
                     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -230,7 +232,7 @@ using namespace b200;
     } while (0)
 
 extern "C" int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t ldx, const int32_t* row_index,
-                                      const void* add, int64_t add_period, const void* gamma, const void* beta,
+                                      const void* neg_row, const void* add, int64_t add_period, const void* gamma, const void* beta,
                                       void* y, int64_t ldy, void* pre_out, float* mean, float* rstd, int64_t rows,
                                       int64_t d, float eps, void* stream) {
     B200_CHECK_CTX(ctx);
@@ -246,8 +248,8 @@ extern "C" int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
 #define CALL(NV)                                                                                                   \
     layernorm_fwd_kernel<NV><<<grid, kLnThreads, 0, st>>>(                                                         \
-        static_cast<const __nv_bfloat16*>(x), ldx, row_index, static_cast<const __nv_bfloat16*>(add),             \
-        static_cast<int>(add ? add_period : 1), static_cast<const __nv_bfloat16*>(gamma),                         \
+        static_cast<const __nv_bfloat16*>(x), ldx, row_index, static_cast<const __nv_bfloat16*>(neg_row),          \
+        static_cast<const __nv_bfloat16*>(add), static_cast<int>(add ? add_period : 1), static_cast<const __nv_bfloat16*>(gamma),                         \
         static_cast<const __nv_bfloat16*>(beta), static_cast<__nv_bfloat16*>(y), ldy,                              \
         static_cast<__nv_bfloat16*>(pre_out), mean, rstd, static_cast<int>(rows), static_cast<int>(d), eps)
     LN_DISPATCH(d, CALL);

@@ -76,7 +76,8 @@ def linear_wgrad(dy, x, out):
 
 
 # ------------------------------------------------------------------------------------- LayerNorm
-def layernorm_fwd(x, gamma, beta, *, rows=None, row_index=None, add=None, add_period=0, out=None, pre_out=None,
+def layernorm_fwd(x, gamma, beta, *, rows=None, row_index=None, neg_row=None, add=None, add_period=0, out=None,
+                  pre_out=None,
                   want_stats=False, eps=1e-5):
     ldx = _row_major(x, "x")
     d = x.shape[1]
@@ -90,7 +91,7 @@ def layernorm_fwd(x, gamma, beta, *, rows=None, row_index=None, add=None, add_pe
         rstd = torch.empty(rows, device=x.device, dtype=f32)
     ctx, st = _ctx_stream(x)
     L.check(L.load().b200clip_layernorm_fwd(
-        ctx, x.data_ptr(), ldx, _ptr(row_index), _ptr(add), add_period, gamma.data_ptr(), beta.data_ptr(),
+        ctx, x.data_ptr(), ldx, _ptr(row_index), _ptr(neg_row), _ptr(add), add_period, gamma.data_ptr(), beta.data_ptr(),
         out.data_ptr(), _row_major(out, "out"), _ptr(pre_out), _ptr(mean), _ptr(rstd), rows, d, eps, st),
         "layernorm_fwd")
     return (out, mean, rstd) if want_stats else out

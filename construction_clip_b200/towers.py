@@ -1,0 +1,194 @@
+"""Forward / backward of the two CLIP towers as sequences of C-ABI kernel launches.
+
+Mirrors upstream ``clip/model.py`` (``VisionTransformer.forward``, ``CLIP.encode_text``,
+``ResidualAttentionBlock.forward``) -- the code the reference reaches through
+``model(image, text)`` (CLIP/train.py:161, CLIP/predict.py:46) and ``model.encode_image``
+(CLIP_prefix_caption/parse_coco.py:43) -- but every operator is one hand-written sm_100a kernel
+(see include/b200clip.h).  Activations are token-major ``[B*S, d]`` bf16 (upstream permutes to
+seq-first LND; the maths is layout independent).
+
+``W`` / ``G`` are dicts ``name -> tensor`` of bf16 weights / fp32 gradient accumulators that use
+upstream's state-dict names relative to the tower prefix.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import torch
+
+from . import lib as L
+from . import ops as O
+
+bf16, f32, i32 = torch.bfloat16, torch.float32, torch.int32
+
+
+@dataclass
+class BlockSaved:
+    x: torch.Tensor = None
+    mean1: torch.Tensor = None
+    rstd1: torch.Tensor = None
+    h1: torch.Tensor = None
+    qkv: torch.Tensor = None
+    a: torch.Tensor = None
+    x2: torch.Tensor = None
+    mean2: torch.Tensor = None
+    rstd2: torch.Tensor = None
+    h2: torch.Tensor = None
+    f: torch.Tensor = None
+    g: torch.Tensor = None
+
+
+@dataclass
+class TowerSaved:
+    blocks: list = field(default_factory=list)
+    extra: dict = field(default_factory=dict)
+
+
+def _blk(prefix: str, i: int) -> str:
+    return f"{prefix}resblocks.{i}."
+
+
+# ------------------------------------------------------------------------------------------------
+# clip.model.ResidualAttentionBlock:  x = x + attn(ln_1(x)) ; x = x + c_proj(QuickGELU(c_fc(ln_2(x))))
+def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None):
+    for i in range(layers):
+        p = _blk(prefix, i)
+        save = saved is not None
+        if save:
+            h1, mean1, rstd1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"], want_stats=True)
+        else:
+            h1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"])
+        qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
+        a = O.attn_fwd(qkv, B, S, H, causal)
+        x2 = O.linear_fwd(a, W[p + "attn.out_proj.weight"], W[p + "attn.out_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x)
+        if save:
+            h2, mean2, rstd2 = O.layernorm_fwd(x2, W[p + "ln_2.weight"], W[p + "ln_2.bias"], want_stats=True)
+            f = torch.empty((x.shape[0], 4 * x.shape[1]), device=x.device, dtype=bf16)
+        else:
+            h2 = O.layernorm_fwd(x2, W[p + "ln_2.weight"], W[p + "ln_2.bias"])
+            f = None
+        g = O.linear_fwd(h2, W[p + "mlp.c_fc.weight"], W[p + "mlp.c_fc.bias"], epilogue=L.EPI_QUICKGELU, preact=f)
+        y = O.linear_fwd(g, W[p + "mlp.c_proj.weight"], W[p + "mlp.c_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x2)
+        if save:
+            saved.blocks.append(BlockSaved(x, mean1, rstd1, h1, qkv, a, x2, mean2, rstd2, h2, f, g))
+        x = y
+    return x
+
+
+def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved):
+    for i in reversed(range(layers)):
+        p = _blk(prefix, i)
+        s: BlockSaved = saved.blocks[i]
+        # ---- MLP branch: y = x2 + c_proj(gelu(c_fc(ln_2(x2))))
+        O.colsum(dy, G[p + "mlp.c_proj.bias"])
+        O.linear_wgrad(dy, s.g, G[p + "mlp.c_proj.weight"])
+        df = O.linear_dgrad(dy, W[p + "mlp.c_proj.weight"], epilogue=L.EPI_QUICKGELU_BWD, aux=s.f)
+        O.colsum(df, G[p + "mlp.c_fc.bias"])
+        O.linear_wgrad(df, s.h2, G[p + "mlp.c_fc.weight"])
+        dh2 = O.linear_dgrad(df, W[p + "mlp.c_fc.weight"])
+        dx2 = O.layernorm_bwd(dh2, s.x2, W[p + "ln_2.weight"], s.mean2, s.rstd2, G[p + "ln_2.weight"],
+                              G[p + "ln_2.bias"], dres=dy)
+        # ---- attention branch: x2 = x + out_proj(attn(in_proj(ln_1(x))))
+        O.colsum(dx2, G[p + "attn.out_proj.bias"])
+        O.linear_wgrad(dx2, s.a, G[p + "attn.out_proj.weight"])
+        da = O.linear_dgrad(dx2, W[p + "attn.out_proj.weight"])
+        dqkv = O.attn_bwd(s.qkv, da, B, S, H, causal)
+        O.colsum(dqkv, G[p + "attn.in_proj_bias"])
+        O.linear_wgrad(dqkv, s.h1, G[p + "attn.in_proj_weight"])
+        dh1 = O.linear_dgrad(dqkv, W[p + "attn.in_proj_weight"])
+        dy = O.layernorm_bwd(dh1, s.x, W[p + "ln_1.weight"], s.mean1, s.rstd1, G[p + "ln_1.weight"],
+                             G[p + "ln_1.bias"], dres=dx2)
+        saved.blocks[i] = None  # release this layer's activations
+    return dy
+
+
+# ------------------------------------------------------------------------------------------------
+def _pool_project_fwd(W, x, row_index, ln_w, ln_b, proj, save):
+    """ln(x[row_index]) @ proj -> fp32 [B, E]   (visual.ln_post + visual.proj / ln_final + text_projection)."""
+    if save:
+        pooled, mean, rstd = O.layernorm_fwd(x, W[ln_w], W[ln_b], row_index=row_index, want_stats=True)
+    else:
+        pooled, mean, rstd = O.layernorm_fwd(x, W[ln_w], W[ln_b], row_index=row_index), None, None
+    feat = O.gemm(pooled, W[proj], b_major=L.MAJOR_MN, out_dtype=f32)  # proj stored [d, E]
+    return feat, (pooled, mean, rstd)
+
+
+def _pool_project_bwd(W, G, dfeat, x, row_index, ln_w, ln_b, proj, pooled, mean, rstd):
+    dfeat_bf = dfeat.contiguous() if dfeat.dtype == bf16 else O.cast_f32_to_bf16(dfeat.contiguous())
+    # dproj[d,E] += pooled^T dfeat ; dpooled = dfeat proj^T
+    O.gemm(pooled, dfeat_bf, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, out=G[proj], split_k=0, accumulate=True)
+    dpooled = O.gemm(dfeat_bf, W[proj])  # B operand = proj [d, E] read K-major (N = d, K = E)
+    dx = torch.zeros_like(x)
+    O.layernorm_bwd(dpooled, x, W[ln_w], mean, rstd, G[ln_w], G[ln_b], row_index=row_index, dx=dx)
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# clip.model.VisionTransformer.forward
+def vision_fwd(W, cfg, image, save: bool):
+    B = image.shape[0]
+    p, n, d = cfg.vision_patch_size, cfg.vision_tokens, cfg.vision_width
+    H = d // 64
+    if image.dtype not in (bf16, f32):
+        image = image.float()
+    image = image.contiguous()
+    kpad = W["conv1.weight"].shape[1]
+    cols = O.im2col_patch(image, p, ldcols=kpad)                      # [B*g*g, kpad]
+    patch = O.gemm(cols, W["conv1.weight"])                           # conv1 as GEMM -> [B*g*g, d]
+    g2 = n - 1
+    ridx = torch.arange(-1, g2, device=image.device, dtype=i32).repeat(B, 1)
+    ridx[:, 1:] += (torch.arange(B, device=image.device, dtype=i32) * g2)[:, None]
+    ridx = ridx.reshape(-1)
+    pre = torch.empty((B * n, d), device=image.device, dtype=bf16) if save else None
+    r = O.layernorm_fwd(patch, W["ln_pre.weight"], W["ln_pre.bias"], rows=B * n, row_index=ridx,
+                        neg_row=W["class_embedding"], add=W["positional_embedding"], add_period=n, pre_out=pre,
+                        want_stats=save)
+    x, mean0, rstd0 = r if save else (r, None, None)
+    saved = TowerSaved() if save else None
+    x = blocks_fwd(W, "transformer.", cfg.vision_layers, x, B, n, H, False, saved)
+    cls_rows = torch.arange(B, device=image.device, dtype=i32) * n
+    feat, head = _pool_project_fwd(W, x, cls_rows, "ln_post.weight", "ln_post.bias", "proj", save)
+    if save:
+        saved.extra = dict(B=B, cols=cols, pre=pre, mean0=mean0, rstd0=rstd0, x_last=x, cls_rows=cls_rows, head=head)
+    return feat, saved
+
+
+def vision_bwd(W, G, cfg, saved: TowerSaved, dfeat):
+    e = saved.extra
+    B, n, d = e["B"], cfg.vision_tokens, cfg.vision_width
+    H = d // 64
+    pooled, mean, rstd = e["head"]
+    dx = _pool_project_bwd(W, G, dfeat, e["x_last"], e["cls_rows"], "ln_post.weight", "ln_post.bias", "proj", pooled,
+                           mean, rstd)
+    dx = blocks_bwd(W, G, "transformer.", cfg.vision_layers, dx, B, n, H, False, saved)
+    dpre = O.layernorm_bwd(dx, e["pre"], W["ln_pre.weight"], e["mean0"], e["rstd0"], G["ln_pre.weight"],
+                           G["ln_pre.bias"])
+    dpatch = O.vision_assemble_bwd(dpre, B, n, G["positional_embedding"], G["class_embedding"])
+    O.linear_wgrad(dpatch, e["cols"], G["conv1.weight"])
+
+
+# ------------------------------------------------------------------------------------------------
+# clip.model.CLIP.encode_text
+def text_fwd(W, cfg, text, save: bool):
+    B, S = text.shape
+    d = cfg.transformer_width
+    H = cfg.transformer_heads
+    ids = text.to(i32).contiguous()
+    x, eot = O.embed_tokens_fwd(ids, W["token_embedding.weight"], W["positional_embedding"])
+    saved = TowerSaved() if save else None
+    x = blocks_fwd(W, "transformer.", cfg.transformer_layers, x, B, S, H, True, saved)
+    feat, head = _pool_project_fwd(W, x, eot, "ln_final.weight", "ln_final.bias", "text_projection", save)
+    if save:
+        saved.extra = dict(B=B, S=S, ids=ids, eot=eot, x_last=x, head=head)
+    return feat, saved
+
+
+def text_bwd(W, G, cfg, saved: TowerSaved, dfeat):
+    e = saved.extra
+    B, S = e["B"], e["S"]
+    H = cfg.transformer_heads
+    pooled, mean, rstd = e["head"]
+    dx = _pool_project_bwd(W, G, dfeat, e["x_last"], e["eot"], "ln_final.weight", "ln_final.bias", "text_projection",
+                           pooled, mean, rstd)
+    dx = blocks_bwd(W, G, "transformer.", cfg.transformer_layers, dx, B, S, H, True, saved)
+    O.embed_tokens_bwd(e["ids"], dx, G["token_embedding.weight"], G["positional_embedding"])

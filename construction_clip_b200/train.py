@@ -1,0 +1,209 @@
+"""Contrastive fine-tune step of CLIP/train.py:157-171 as one fused call, data parallel over
+``torch.distributed`` (one process per GPU, NCCL over NVLink).
+
+  model.zero_grad(); logits = model(image, text); loss = (CE(lpi)+CE(lpt))/2;
+  loss.backward(); optimizer.step(); scheduler.step()
+
+becomes ``ClipTrainer.step(image, text)``:
+  * each rank encodes its slice of the global batch (both towers, hand-written kernels),
+  * the L2-normalised embeddings are all-gathered (the ONE data-path collective of the forward),
+  * the fused similarity + softmax-CE kernel computes this rank's rows of the global Bg x Bg
+    problem without writing the logits; row log-sum-exps are all-gathered so that every rank can
+    form the EXACT gradient of the global loss w.r.t. its own embeddings (no gradient collective
+    for activations),
+  * backward kernels fill a flat fp32 gradient buffer per tower, which is sum-all-reduced
+    (overlapped with the other tower's backward) and consumed by the fused AdamW kernel
+    (fp32 master weights, bf16 shadow = the tensors the forward kernels read).
+
+``clip_contrastive_loss`` exposes the same fused, distributed loss as an autograd op for callers
+that keep their own optimiser (``loss.backward()`` then fills ``.grad`` of the local replica with
+the gradient of the GLOBAL loss for the local samples; sum-reduce across ranks).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+
+from . import ops as O
+from . import towers as T
+
+bf16, f32 = torch.bfloat16, torch.float32
+
+
+def _world(group):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def _all_gather_rows(x, group, world):
+    """[Bl, E] per rank -> [world*Bl, E] (rank-major), NCCL all-gather."""
+    if world == 1:
+        return x
+    out = torch.empty((world * x.shape[0], *x.shape[1:]), device=x.device, dtype=x.dtype)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
+class _LossState:
+    """Forward of the fused loss on normalised local features; keeps what backward needs."""
+
+    def __init__(self, img_f, txt_f, logit_scale, group):
+        world, rank = _world(group)
+        self.world, self.rank, self.group = world, rank, group
+        Bl, E = img_f.shape
+        self.Bl, self.Bg, self.E = Bl, Bl * world, E
+        self.row0 = rank * Bl
+        self.ls = logit_scale.detach().to(f32).reshape(1).contiguous()
+        self.img_n, self.inv_i = O.l2norm_fwd(img_f.contiguous())
+        self.txt_n, self.inv_t = O.l2norm_fwd(txt_f.contiguous())
+        if world > 1:
+            both = _all_gather_rows(torch.cat([self.img_n, self.txt_n], dim=1), group, world)  # [Bg, 2E]
+            self.img_all = both[:, :E].contiguous()
+            self.txt_all = both[:, E:].contiguous()
+        else:
+            self.img_all, self.txt_all = self.img_n, self.txt_n
+        self.ws = O.clip_loss_workspace(img_f.device, Bl, self.Bg, E)
+        lse_i, lse_t, loss_sum, correct = O.clip_loss_fwd(self.img_all, self.txt_all, self.ls, self.row0, Bl, self.ws)
+        if world > 1:
+            lse = _all_gather_rows(torch.stack([lse_i, lse_t], dim=1), group, world)  # [Bg, 2]
+            self.lse_i_all, self.lse_t_all = lse[:, 0].contiguous(), lse[:, 1].contiguous()
+            stats = torch.cat([loss_sum, correct.to(f32)])
+            dist.all_reduce(stats, group=group)
+            loss_sum, self.correct = stats[:2], stats[2]
+        else:
+            self.lse_i_all, self.lse_t_all = lse_i, lse_t
+            self.correct = correct.to(f32)[0]
+        self.loss = (loss_sum[0] + loss_sum[1]) / (2.0 * self.Bg)  # global mean loss, same on every rank
+
+    def backward(self, grad_out=None):
+        """-> (d_img_f bf16 [Bl,E], d_txt_f bf16 [Bl,E], d_logit_scale fp32 [1], local share)."""
+        d_img_n, d_txt_n, d_ls = O.clip_loss_bwd(self.img_all, self.txt_all, self.ls, self.lse_i_all, self.lse_t_all,
+                                                 grad_out, self.row0, self.Bl, self.ws)
+        d_img = O.l2norm_bwd(d_img_n, self.img_n, self.inv_i)
+        d_txt = O.l2norm_bwd(d_txt_n, self.txt_n, self.inv_t)
+        return d_img, d_txt, d_ls
+
+
+class _FusedLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, img_f, txt_f, logit_scale, group):
+        st = _LossState(img_f, txt_f, logit_scale, group)
+        ctx.st = st
+        ctx.ls_dtype = logit_scale.dtype
+        ctx.mark_non_differentiable(st.correct)
+        return st.loss, st.correct
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_correct):
+        g = grad_loss.detach().to(f32).reshape(1).contiguous()
+        d_img, d_txt, d_ls = ctx.st.backward(g)
+        ctx.st = None
+        return d_img.float(), d_txt.float(), d_ls.reshape(()).to(ctx.ls_dtype), None
+
+
+def clip_contrastive_loss(model, image, text, group=None, return_correct=False):
+    """Fused symmetric InfoNCE over the GLOBAL batch (all ranks of ``group``); differentiable."""
+    img_f = model._features("visual", image)
+    txt_f = model._features("text", text)
+    loss, correct = _FusedLossFn.apply(img_f, txt_f, model.logit_scale, group)
+    return (loss, correct) if return_correct else loss
+
+
+# ------------------------------------------------------------------------------------------------
+class ClipTrainer:
+    """Owns flat fp32 gradients / master weights / Adam moments for both towers and runs the
+    whole training step with library kernels.  Hyper-parameters default to the reference's
+    ``AdamW(lr=1e-5)`` from transformers (betas 0.9/0.999, eps 1e-6, no weight decay) and
+    ``get_linear_schedule_with_warmup(5000, total)`` (CLIP/train.py:143-147)."""
+
+    def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, warmup_steps=5000,
+                 total_steps=None, group=None, device=None):
+        self.model = model
+        self.cfg = model.cfg
+        self.group = group
+        self.world, self.rank = _world(group)
+        self.device = torch.device(device) if device is not None else next(model.parameters()).device
+        self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
+        self.warmup_steps, self.total_steps = warmup_steps, total_steps
+        self.step_count = 0
+        self.stores = {k: model._store(k, self.device) for k in ("visual", "text")}
+        self.grads, self.master, self.m, self.v = {}, {}, {}, {}
+        for k, st in self.stores.items():
+            st.sync()
+            self.grads[k] = torch.zeros(st.total, device=self.device, dtype=f32)
+            self.master[k] = st.w.float()
+            self.m[k] = torch.zeros_like(self.grads[k])
+            self.v[k] = torch.zeros_like(self.grads[k])
+        self.G = {k: self.stores[k].grad_views(self.grads[k]) for k in self.stores}
+        self.ls_master = model.logit_scale.detach().to(f32).reshape(1).clone()
+        self.ls_m = torch.zeros(1, device=self.device, dtype=f32)
+        self.ls_v = torch.zeros(1, device=self.device, dtype=f32)
+        self.last_correct = None
+
+    def current_lr(self):
+        # lr used by the k-th optimizer.step() (k = 0, 1, ...) under LambdaLR: lr * lambda(k)
+        s = self.step_count - 1
+        if self.warmup_steps and s < self.warmup_steps:
+            return self.lr * s / max(1, self.warmup_steps)
+        if self.total_steps:
+            return self.lr * max(0.0, (self.total_steps - s) / max(1, self.total_steps - self.warmup_steps))
+        return self.lr
+
+    def forward_backward(self, image, text):
+        """Fills the flat gradient buffers with d(global loss)/d(params); returns the loss tensor."""
+        cfg = self.cfg
+        for k in self.grads:
+            self.grads[k].zero_()
+        Wv, Wt = self.stores["visual"].W, self.stores["text"].W
+        img_f, saved_i = T.vision_fwd(Wv, cfg, image, True)
+        txt_f, saved_t = T.text_fwd(Wt, cfg, text, True)
+        st = _LossState(img_f, txt_f, self.ls_master, self.group)
+        d_img, d_txt, d_ls = st.backward(None)
+        work = []
+        T.vision_bwd(Wv, self.G["visual"], cfg, saved_i, d_img)
+        if self.world > 1:
+            work.append(dist.all_reduce(self.grads["visual"], group=self.group, async_op=True))
+        T.text_bwd(Wt, self.G["text"], cfg, saved_t, d_txt)
+        if self.world > 1:
+            work.append(dist.all_reduce(self.grads["text"], group=self.group, async_op=True))
+            work.append(dist.all_reduce(d_ls, group=self.group, async_op=True))
+            for w in work:
+                w.wait()
+        self.d_ls = d_ls
+        self.last_correct = st.correct
+        return st.loss
+
+    def optimizer_step(self):
+        self.step_count += 1
+        lr = self.current_lr()
+        b1, b2 = self.betas
+        for k, st in self.stores.items():
+            O.adamw(self.master[k], st.w, self.grads[k], self.m[k], self.v[k], lr=lr, beta1=b1, beta2=b2, eps=self.eps,
+                    weight_decay=self.wd, grad_scale=1.0, step=self.step_count)
+        O.adamw(self.ls_master, None, self.d_ls, self.ls_m, self.ls_v, lr=lr, beta1=b1, beta2=b2, eps=self.eps,
+                weight_decay=self.wd, grad_scale=1.0, step=self.step_count)
+        with torch.no_grad():
+            self.model.logit_scale.copy_(self.ls_master.reshape(()))
+
+    def write_back(self):
+        """Copies the fp32 master weights into parameters that are not views of the bf16 shadow
+        (e.g. after ``model.float()``); linked bf16 parameters are already up to date."""
+        with torch.no_grad():
+            for k, st in self.stores.items():
+                for name, p, o, s in st.entries:
+                    if p.data_ptr() != st.W[name].data_ptr():
+                        n = math.prod(s)
+                        src = self.master[k][o:o + n].view(s)
+                        if tuple(s) != tuple(p.shape):
+                            src = src[:, :math.prod(p.shape[1:])]
+                        p.copy_(src.reshape(p.shape))
+
+    def step(self, image, text):
+        """One optimisation step on this rank's slice (image [Bl,3,R,R], text [Bl,77]) of the
+        global batch; returns the global mean loss as a device tensor (no host sync)."""
+        loss = self.forward_backward(image, text)
+        self.optimizer_step()
+        return loss

@@ -91,14 +91,16 @@ int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda, int a_majo
 
 /* ---- clip.model.LayerNorm (fp32 statistics, eps, affine) ------------------------------------
  * y[r,:] = LN(x[src(r),:]) * gamma + beta ; src(r) = row_index ? row_index[r] : r.
+ * A negative src(r) reads neg_row (bf16 [d]; zeros when NULL) instead of x -- the class token.
  * Optional fused add before normalisation (vision token assembly, replaces
  * cat(class_embedding, conv) + positional_embedding + ln_pre):
  *   v = x[src(r),:] + add[(r % add_period),:]   when add != NULL.
  * If pre_out != NULL the pre-normalisation value v is also stored (bf16, ldy pitch).
  * mean/rstd: fp32 [rows] or NULL. */
-int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t ldx, const int32_t* row_index, const void* add,
-                           int64_t add_period, const void* gamma, const void* beta, void* y, int64_t ldy,
-                           void* pre_out, float* mean, float* rstd, int64_t rows, int64_t d, float eps, void* stream);
+int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t ldx, const int32_t* row_index,
+                           const void* neg_row, const void* add, int64_t add_period, const void* gamma,
+                           const void* beta, void* y, int64_t ldy, void* pre_out, float* mean, float* rstd,
+                           int64_t rows, int64_t d, float eps, void* stream);
 /* dx[dst(r),:] = (dres ? dres[r,:] : 0) + LN'(dy[r,:]) ; dgamma/dbeta fp32 [d] ACCUMULATED (atomics).
  * x is read with the same src(r) mapping as the forward; dx is written at dst(r) = src(r). */
 int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t lddy, const void* x, int64_t ldx,

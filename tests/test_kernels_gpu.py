@@ -125,12 +125,14 @@ def test_layernorm_gather_and_assemble(ops):
     # vision token assembly: row (b,t): t==0 -> cls+pos[0] ; else patch[b,t-1] + pos[t]
     patch = _rand((B * (n - 1), d), seed=4)
     poscls = _rand((n, d), seed=5)
+    cls = _rand((d,), seed=6)
     ridx = torch.full((B, n), -1, dtype=torch.int32, device="cuda")
     ridx[:, 1:] = (torch.arange(B, device="cuda")[:, None] * (n - 1) + torch.arange(n - 1, device="cuda")[None]).int()
     pre = torch.empty((B * n, d), device="cuda", dtype=bf16)
-    y = ops.layernorm_fwd(patch, g, b, rows=B * n, row_index=ridx.reshape(-1).contiguous(), add=poscls, add_period=n,
+    y = ops.layernorm_fwd(patch, g, b, rows=B * n, row_index=ridx.reshape(-1).contiguous(), neg_row=cls, add=poscls,
+                          add_period=n,
                           pre_out=pre)
-    full = torch.cat([torch.zeros(B, 1, d, device="cuda"), patch.float().view(B, n - 1, d)], 1) + poscls.float()
+    full = torch.cat([cls.float().expand(B, 1, d), patch.float().view(B, n - 1, d)], 1) + poscls.float()
     _close(pre, full.view(-1, d), 2e-2, 1e-2, "assemble pre")
     _close(y, torch.nn.functional.layer_norm(pre.float(), (d,), g.float(), b.float(), 1e-5), 2e-2, 1e-2, "assemble ln")
 
