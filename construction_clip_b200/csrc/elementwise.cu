@@ -9,9 +9,10 @@ namespace b200 {
 
 // ------------------------------------------------------------------------------------------------
 // token_embedding(text) + positional_embedding       (clip.model.CLIP.encode_text, first two lines)
+template <typename TOut>
 __global__ void __launch_bounds__(256)
 embed_tokens_fwd_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
-                        const __nv_bfloat16* __restrict__ pos, __nv_bfloat16* __restrict__ out, int rows, int S, int d,
+                        const __nv_bfloat16* __restrict__ pos, TOut* __restrict__ out, int rows, int S, int d,
                         int vocab) {
     const int lane = threadIdx.x & 31;
     const int nvec = d >> 3;
@@ -23,13 +24,21 @@ embed_tokens_fwd_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __
             const uint4 a = __ldg(reinterpret_cast<const uint4*>(table + static_cast<int64_t>(id) * d + vec * 8));
             const uint4 b = __ldg(reinterpret_cast<const uint4*>(pos + static_cast<int64_t>(s) * d + vec * 8));
             const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w};
-            uint32_t ow[4];
+            float o[8];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const float2 fa = unpack_bf16(aw[j]), fb = unpack_bf16(bw[j]);
-                ow[j] = pack_bf16(fa.x + fb.x, fa.y + fb.y);
+                o[2 * j] = fa.x + fb.x;
+                o[2 * j + 1] = fa.y + fb.y;
             }
-            *reinterpret_cast<uint4*>(out + static_cast<int64_t>(r) * d + vec * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+            TOut* dst = out + static_cast<int64_t>(r) * d + vec * 8;
+            if constexpr (sizeof(TOut) == 2) {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
+                                                            pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            } else {
+                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
         }
     }
 }
@@ -317,16 +326,23 @@ static inline int grid_for(int64_t n, int threads, int num_sms, int per_sm = 8) 
 using namespace b200;
 
 extern "C" int b200clip_embed_tokens_fwd(b200clip_ctx* ctx, const int32_t* ids, const void* table, const void* pos,
-                                         void* out, int32_t* eot_row, int64_t B, int64_t S, int64_t d, int64_t vocab,
-                                         void* stream) {
+                                         void* out, int out_dtype, int32_t* eot_row, int64_t B, int64_t S, int64_t d,
+                                         int64_t vocab, void* stream) {
     B200_CHECK_CTX(ctx);
     B200_CHECK_ARG(ids && table && pos && out, "embed_tokens_fwd: null pointer");
     B200_CHECK_ARG(B > 0 && S > 0 && d > 0 && d % 8 == 0 && vocab > 0 && B * S < (1ll << 31), "embed_tokens_fwd: bad shape");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int rows = static_cast<int>(B * S);
-    embed_tokens_fwd_kernel<<<grid_for(ceil_div(rows, 8) * 256, 256, ctx->num_sms), 256, 0, st>>>(
-        ids, static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(pos),
-        static_cast<__nv_bfloat16*>(out), rows, static_cast<int>(S), static_cast<int>(d), static_cast<int>(vocab));
+    B200_CHECK_ARG(out_dtype == B200CLIP_DT_BF16 || out_dtype == B200CLIP_DT_F32, "embed_tokens_fwd: bad out_dtype");
+    const int grid = grid_for(ceil_div(rows, 8) * 256, 256, ctx->num_sms);
+    if (out_dtype == B200CLIP_DT_BF16)
+        embed_tokens_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+            ids, static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(pos),
+            static_cast<__nv_bfloat16*>(out), rows, static_cast<int>(S), static_cast<int>(d), static_cast<int>(vocab));
+    else
+        embed_tokens_fwd_kernel<float><<<grid, 256, 0, st>>>(
+            ids, static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(pos),
+            static_cast<float*>(out), rows, static_cast<int>(S), static_cast<int>(d), static_cast<int>(vocab));
     B200_LAUNCH_CHECK();
     if (eot_row != nullptr) {
         eot_argmax_kernel<<<static_cast<int>(ceil_div(B, 8)), 256, 0, st>>>(ids, eot_row, static_cast<int>(B),

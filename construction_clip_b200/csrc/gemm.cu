@@ -79,6 +79,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) x[i] = quick_gelu(x[i]);
+        } else if constexpr (EPI == B200CLIP_EPI_RESIDUAL && OUT_F32) {
+            // fp32 residual stream: aux and C are fp32
+            const float* ap = reinterpret_cast<const float*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col;
+            const float4 a0 = *reinterpret_cast<const float4*>(ap);
+            const float4 a1 = *reinterpret_cast<const float4*>(ap + 4);
+            x[0] += a0.x; x[1] += a0.y; x[2] += a0.z; x[3] += a0.w;
+            x[4] += a1.x; x[5] += a1.y; x[6] += a1.z; x[7] += a1.w;
         } else if constexpr (EPI == B200CLIP_EPI_RESIDUAL || EPI == B200CLIP_EPI_QUICKGELU_BWD) {
             const uint4 a = *reinterpret_cast<const uint4*>(p.aux + static_cast<int64_t>(row) * p.ldaux + col);
             const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
@@ -117,7 +124,9 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
 __device__ __forceinline__ void epilogue_dispatch(const GemmParams& p, const uint32_t (&acc)[32], int row, int col0,
                                                   float scale) {
     if (p.out_f32) {
-        if (p.atomic_out)
+        if (p.epilogue == B200CLIP_EPI_RESIDUAL)
+            epilogue_chunk<B200CLIP_EPI_RESIDUAL, true, false>(p, acc, row, col0, scale);
+        else if (p.atomic_out)
             epilogue_chunk<B200CLIP_EPI_NONE, true, true>(p, acc, row, col0, scale);
         else
             epilogue_chunk<B200CLIP_EPI_NONE, true, false>(p, acc, row, col0, scale);
@@ -391,7 +400,10 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
     B200_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm: bad epilogue %d", epilogue);
     const bool out_f32 = out_dtype == B200CLIP_DT_F32;
     if (out_f32) {
-        B200_CHECK_ARG(epilogue == B200CLIP_EPI_NONE, "gemm: fp32 output supports EPI_NONE only");
+        B200_CHECK_ARG(epilogue == B200CLIP_EPI_NONE || epilogue == B200CLIP_EPI_RESIDUAL,
+                       "gemm: fp32 output supports EPI_NONE / EPI_RESIDUAL only");
+        B200_CHECK_ARG(epilogue == B200CLIP_EPI_NONE || (split_k == 1 && !accumulate),
+                       "gemm: EPI_RESIDUAL with fp32 output needs split_k = 1 and no accumulate");
         B200_CHECK_ARG(ldc % 4 == 0 && (reinterpret_cast<uintptr_t>(C) & 15) == 0, "gemm: fp32 C not 16B aligned");
     } else {
         B200_CHECK_ARG(split_k <= 1 && !accumulate, "gemm: split_k / accumulate need fp32 output");
@@ -399,7 +411,8 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
     }
     if (epilogue == B200CLIP_EPI_RESIDUAL || epilogue == B200CLIP_EPI_QUICKGELU_BWD) {
         B200_CHECK_ARG(aux != nullptr, "gemm: epilogue %d needs aux", epilogue);
-        B200_CHECK_ARG(ldaux % 8 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, "gemm: aux not 16B aligned");
+        B200_CHECK_ARG(ldaux % (out_f32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0,
+                       "gemm: aux not 16B aligned");
     }
     B200_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias not 16B aligned");
     B200_CHECK_ARG(preact == nullptr || (reinterpret_cast<uintptr_t>(preact) & 15) == 0, "gemm: preact misaligned");
@@ -421,7 +434,7 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
 
     // tile width: 256 when that still fills the machine, else 128 for more CTAs
     const int64_t tiles256 = ceil_div(M, BM) * ceil_div(N, 256);
-    const bool use256 = (N >= 256) && (tiles256 >= ctx->num_sms || out_f32);
+    const bool use256 = (N >= 256) && (tiles256 >= ctx->num_sms || (out_f32 && epilogue == B200CLIP_EPI_NONE));
     const int64_t tiles = use256 ? tiles256 : ceil_div(M, BM) * ceil_div(N, 128);
     if (split_k <= 0) split_k = out_f32 ? choose_split_k(tiles, p.kb_total, ctx->num_sms) : 1;
     if (split_k > p.kb_total) split_k = p.kb_total;

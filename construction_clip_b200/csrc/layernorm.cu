@@ -11,12 +11,42 @@ namespace b200 {
 
 constexpr int kLnThreads = 256;  // 8 rows per block
 
-template <int NV>  // NV = uint4 vectors (8 bf16) per lane, covers d <= NV*256
+// 8 consecutive elements <-> 8 floats, for bf16 or fp32 storage
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&f)[8]) {
+    if constexpr (sizeof(T) == 2) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 t = unpack_bf16(w[j]);
+            f[2 * j] = t.x;
+            f[2 * j + 1] = t.y;
+        }
+    } else {
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        const float4 b = *reinterpret_cast<const float4*>(p + 4);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+        f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+    }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float (&f)[8]) {
+    if constexpr (sizeof(T) == 2) {
+        *reinterpret_cast<uint4*>(p) =
+            make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    } else {
+        *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+        *reinterpret_cast<float4*>(p + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+}
+
+template <int NV, typename TX, typename TY>  // NV = 8-element vectors per lane, covers d <= NV*256
 __global__ void __launch_bounds__(kLnThreads)
-layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int32_t* __restrict__ row_index,
+layernorm_fwd_kernel(const TX* __restrict__ x, int64_t ldx, const int32_t* __restrict__ row_index,
                      const __nv_bfloat16* __restrict__ neg_row, const __nv_bfloat16* __restrict__ add, int add_period,
                      const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
-                     __nv_bfloat16* __restrict__ y, int64_t ldy,
+                     TY* __restrict__ y, int64_t ldy,
                      __nv_bfloat16* __restrict__ pre_out, float* __restrict__ mean_out, float* __restrict__ rstd_out,
                      int rows, int d, float eps) {
     const int lane = threadIdx.x & 31;
@@ -32,16 +62,10 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int
 #pragma unroll
             for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
             if (vec < nvec) {
-                if (src >= 0 || neg_row != nullptr) {
-                    const uint4 u = (src >= 0) ? *reinterpret_cast<const uint4*>(x + src * ldx + vec * 8)
-                                               : __ldg(reinterpret_cast<const uint4*>(neg_row + vec * 8));
-                    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = unpack_bf16(w[j]);
-                        v[i][2 * j] = f.x;
-                        v[i][2 * j + 1] = f.y;
-                    }
+                if (src >= 0) {
+                    load8(x + src * ldx + vec * 8, v[i]);
+                } else if (neg_row != nullptr) {
+                    load8(neg_row + vec * 8, v[i]);
                 }
                 if (add != nullptr) {
                     const uint4 u = __ldg(reinterpret_cast<const uint4*>(add + static_cast<int64_t>(r % add_period) * d + vec * 8));
@@ -95,28 +119,21 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const int
         for (int i = 0; i < NV; ++i) {
             const int vec = lane + 32 * i;
             if (vec < nvec) {
-                const uint4 g = __ldg(reinterpret_cast<const uint4*>(gamma + vec * 8));
-                const uint4 b = __ldg(reinterpret_cast<const uint4*>(beta + vec * 8));
-                const uint32_t gw[4] = {g.x, g.y, g.z, g.w};
-                const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-                uint32_t ow[4];
+                float gf[8], bf[8], o[8];
+                load8(gamma + vec * 8, gf);
+                load8(beta + vec * 8, bf);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 gf = unpack_bf16(gw[j]);
-                    const float2 bf = unpack_bf16(bw[j]);
-                    ow[j] = pack_bf16((v[i][2 * j] - mean) * rstd * gf.x + bf.x,
-                                      (v[i][2 * j + 1] - mean) * rstd * gf.y + bf.y);
-                }
-                *reinterpret_cast<uint4*>(y + static_cast<int64_t>(r) * ldy + vec * 8) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                for (int j = 0; j < 8; ++j) o[j] = (v[i][j] - mean) * rstd * gf[j] + bf[j];
+                store8(y + static_cast<int64_t>(r) * ldy + vec * 8, o);
             }
         }
     }
 }
 
 // dx = dres + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma,  xhat = (x-mean)*rstd
-template <int NV>
+template <int NV, typename TX>
 __global__ void __launch_bounds__(kLnThreads)
-layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const __nv_bfloat16* __restrict__ x,
+layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const TX* __restrict__ x,
                      int64_t ldx, const int32_t* __restrict__ row_index, const __nv_bfloat16* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const __nv_bfloat16* __restrict__ dres, int64_t lddres, __nv_bfloat16* __restrict__ dx,
@@ -142,25 +159,16 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const _
         for (int i = 0; i < NV; ++i) {
             const int vec = lane + 32 * i;
             if (vec < nvec) {
-                const uint4 ux = *reinterpret_cast<const uint4*>(x + src * ldx + vec * 8);
-                const uint4 ud = *reinterpret_cast<const uint4*>(dy + static_cast<int64_t>(r) * lddy + vec * 8);
-                const uint4 ug = __ldg(reinterpret_cast<const uint4*>(gamma + vec * 8));
-                const uint32_t xw[4] = {ux.x, ux.y, ux.z, ux.w};
-                const uint32_t dw[4] = {ud.x, ud.y, ud.z, ud.w};
-                const uint32_t gw[4] = {ug.x, ug.y, ug.z, ug.w};
+                float xf[8], df[8], gf[8];
+                load8(x + src * ldx + vec * 8, xf);
+                load8(dy + static_cast<int64_t>(r) * lddy + vec * 8, df);
+                load8(gamma + vec * 8, gf);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 xf = unpack_bf16(xw[j]);
-                    const float2 df = unpack_bf16(dw[j]);
-                    const float2 gf = unpack_bf16(gw[j]);
-                    xh[i][2 * j] = (xf.x - mu) * rs;
-                    xh[i][2 * j + 1] = (xf.y - mu) * rs;
-                    ab[i][2 * j] += df.x;
-                    ab[i][2 * j + 1] += df.y;
-                    ag[i][2 * j] += df.x * xh[i][2 * j];
-                    ag[i][2 * j + 1] += df.y * xh[i][2 * j + 1];
-                    g[i][2 * j] = df.x * gf.x;
-                    g[i][2 * j + 1] = df.y * gf.y;
+                for (int j = 0; j < 8; ++j) {
+                    xh[i][j] = (xf[j] - mu) * rs;
+                    ab[i][j] += df[j];
+                    ag[i][j] += df[j] * xh[i][j];
+                    g[i][j] = df[j] * gf[j];
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -234,26 +242,41 @@ using namespace b200;
 extern "C" int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t ldx, const int32_t* row_index,
                                       const void* neg_row, const void* add, int64_t add_period, const void* gamma, const void* beta,
                                       void* y, int64_t ldy, void* pre_out, float* mean, float* rstd, int64_t rows,
-                                      int64_t d, float eps, void* stream) {
+                                      int64_t d, float eps, int x_dtype, int y_dtype, void* stream) {
     B200_CHECK_CTX(ctx);
     B200_CHECK_ARG(x && gamma && beta && y, "layernorm_fwd: null pointer");
     B200_CHECK_ARG(rows > 0 && rows < (1ll << 31), "layernorm_fwd: bad rows %lld", (long long)rows);
     B200_CHECK_ARG(d >= 8 && d <= 2048 && d % 8 == 0, "layernorm_fwd: d=%lld must be a multiple of 8 in [8,2048]",
                    (long long)d);
-    B200_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0, "layernorm_fwd: row pitches must be multiples of 8");
+    B200_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0, "layernorm_fwd: row pitches must be multiples of 8 elements");
     B200_CHECK_ARG(add == nullptr || add_period > 0, "layernorm_fwd: add_period must be > 0");
     const int wpb = kLnThreads / 32;
     const int64_t want = ceil_div(rows, wpb);
     const int grid = static_cast<int>(want < ctx->num_sms * 8 ? want : ctx->num_sms * 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CALL(NV)                                                                                                   \
-    layernorm_fwd_kernel<NV><<<grid, kLnThreads, 0, st>>>(                                                         \
-        static_cast<const __nv_bfloat16*>(x), ldx, row_index, static_cast<const __nv_bfloat16*>(neg_row),          \
-        static_cast<const __nv_bfloat16*>(add), static_cast<int>(add ? add_period : 1), static_cast<const __nv_bfloat16*>(gamma),                         \
-        static_cast<const __nv_bfloat16*>(beta), static_cast<__nv_bfloat16*>(y), ldy,                              \
-        static_cast<__nv_bfloat16*>(pre_out), mean, rstd, static_cast<int>(rows), static_cast<int>(d), eps)
+    B200_CHECK_ARG((x_dtype == B200CLIP_DT_BF16 || x_dtype == B200CLIP_DT_F32) &&
+                       (y_dtype == B200CLIP_DT_BF16 || y_dtype == B200CLIP_DT_F32), "layernorm_fwd: bad dtype");
+#define CALL_T(NV, TX, TY)                                                                                         \
+    layernorm_fwd_kernel<NV, TX, TY><<<grid, kLnThreads, 0, st>>>(                                                 \
+        static_cast<const TX*>(x), ldx, row_index, static_cast<const __nv_bfloat16*>(neg_row),                     \
+        static_cast<const __nv_bfloat16*>(add), static_cast<int>(add ? add_period : 1),                            \
+        static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), static_cast<TY*>(y),    \
+        ldy, static_cast<__nv_bfloat16*>(pre_out), mean, rstd, static_cast<int>(rows), static_cast<int>(d), eps)
+#define CALL(NV)                                                                       \
+    do {                                                                               \
+        if (x_dtype == B200CLIP_DT_BF16 && y_dtype == B200CLIP_DT_BF16) {              \
+            CALL_T(NV, __nv_bfloat16, __nv_bfloat16);                                  \
+        } else if (x_dtype == B200CLIP_DT_BF16) {                                      \
+            CALL_T(NV, __nv_bfloat16, float);                                          \
+        } else if (y_dtype == B200CLIP_DT_BF16) {                                      \
+            CALL_T(NV, float, __nv_bfloat16);                                          \
+        } else {                                                                       \
+            CALL_T(NV, float, float);                                                  \
+        }                                                                              \
+    } while (0)
     LN_DISPATCH(d, CALL);
 #undef CALL
+#undef CALL_T
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -261,7 +284,8 @@ extern "C" int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t 
 extern "C" int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t lddy, const void* x, int64_t ldx,
                                       const int32_t* row_index, const void* gamma, const float* mean,
                                       const float* rstd, const void* dres, int64_t lddres, void* dx, int64_t lddx,
-                                      float* dgamma, float* dbeta, int64_t rows, int64_t d, void* stream) {
+                                      float* dgamma, float* dbeta, int64_t rows, int64_t d, int x_dtype,
+                                      void* stream) {
     B200_CHECK_CTX(ctx);
     B200_CHECK_ARG(dy && x && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
     B200_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must come together");
@@ -274,11 +298,20 @@ extern "C" int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t
     const int grid = static_cast<int>(want < ctx->num_sms * 4 ? (want > 0 ? want : 1) : ctx->num_sms * 4);
     const size_t smem = 2 * d * sizeof(float);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define CALL(NV)                                                                                                    \
-    layernorm_bwd_kernel<NV><<<grid, kLnThreads, smem, st>>>(                                                       \
-        static_cast<const __nv_bfloat16*>(dy), lddy, static_cast<const __nv_bfloat16*>(x), ldx, row_index,         \
+    B200_CHECK_ARG(x_dtype == B200CLIP_DT_BF16 || x_dtype == B200CLIP_DT_F32, "layernorm_bwd: bad x dtype");
+#define CALL_T(NV, TX)                                                                                              \
+    layernorm_bwd_kernel<NV, TX><<<grid, kLnThreads, smem, st>>>(                                                   \
+        static_cast<const __nv_bfloat16*>(dy), lddy, static_cast<const TX*>(x), ldx, row_index,                    \
         static_cast<const __nv_bfloat16*>(gamma), mean, rstd, static_cast<const __nv_bfloat16*>(dres), lddres,     \
         static_cast<__nv_bfloat16*>(dx), lddx, dgamma, dbeta, static_cast<int>(rows), static_cast<int>(d))
+#define CALL(NV)                                  \
+    do {                                          \
+        if (x_dtype == B200CLIP_DT_BF16) {        \
+            CALL_T(NV, __nv_bfloat16);            \
+        } else {                                  \
+            CALL_T(NV, float);                    \
+        }                                         \
+    } while (0)
     LN_DISPATCH(d, CALL);
 #undef CALL
     B200_LAUNCH_CHECK();

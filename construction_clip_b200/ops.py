@@ -23,6 +23,14 @@ def _ptr(t):
     return None if t is None else t.data_ptr()
 
 
+def _dt(t):
+    if t.dtype == bf16:
+        return L.DT_BF16
+    if t.dtype == f32:
+        return L.DT_F32
+    raise RuntimeError(f"unsupported dtype {t.dtype}")
+
+
 def _row_major(t: torch.Tensor, name: str):
     if t.dim() != 2 or t.stride(1) != 1:
         raise RuntimeError(f"{name}: expected a 2-D tensor with unit inner stride, got {tuple(t.shape)} strides {t.stride()}")
@@ -77,14 +85,13 @@ def linear_wgrad(dy, x, out):
 
 # ------------------------------------------------------------------------------------- LayerNorm
 def layernorm_fwd(x, gamma, beta, *, rows=None, row_index=None, neg_row=None, add=None, add_period=0, out=None,
-                  pre_out=None,
-                  want_stats=False, eps=1e-5):
+                  pre_out=None, want_stats=False, eps=1e-5, out_dtype=bf16):
     ldx = _row_major(x, "x")
     d = x.shape[1]
     if rows is None:
         rows = row_index.numel() if row_index is not None else x.shape[0]
     if out is None:
-        out = torch.empty((rows, d), device=x.device, dtype=bf16)
+        out = torch.empty((rows, d), device=x.device, dtype=out_dtype)
     mean = rstd = None
     if want_stats:
         mean = torch.empty(rows, device=x.device, dtype=f32)
@@ -92,7 +99,8 @@ def layernorm_fwd(x, gamma, beta, *, rows=None, row_index=None, neg_row=None, ad
     ctx, st = _ctx_stream(x)
     L.check(L.load().b200clip_layernorm_fwd(
         ctx, x.data_ptr(), ldx, _ptr(row_index), _ptr(neg_row), _ptr(add), add_period, gamma.data_ptr(), beta.data_ptr(),
-        out.data_ptr(), _row_major(out, "out"), _ptr(pre_out), _ptr(mean), _ptr(rstd), rows, d, eps, st),
+        out.data_ptr(), _row_major(out, "out"), _ptr(pre_out), _ptr(mean), _ptr(rstd), rows, d, eps, _dt(x), _dt(out),
+        st),
         "layernorm_fwd")
     return (out, mean, rstd) if want_stats else out
 
@@ -106,7 +114,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, *, row_index=None, dr
         ctx, dy.data_ptr(), _row_major(dy, "dy"), x.data_ptr(), _row_major(x, "x"), _ptr(row_index),
         gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(dres),
         _row_major(dres, "dres") if dres is not None else 0, dx.data_ptr(), _row_major(dx, "dx"),
-        _ptr(dgamma), _ptr(dbeta), rows, d, st), "layernorm_bwd")
+        _ptr(dgamma), _ptr(dbeta), rows, d, _dt(x), st), "layernorm_bwd")
     return dx
 
 
@@ -131,15 +139,15 @@ def attn_bwd(qkv, dout, B, S, H, causal, dqkv=None):
 
 
 # ------------------------------------------------------------------------------------- embedding
-def embed_tokens_fwd(ids, table, pos):
+def embed_tokens_fwd(ids, table, pos, out_dtype=bf16):
     B, S = ids.shape
     V, d = table.shape
     assert ids.dtype == i32 and ids.is_contiguous() and table.is_contiguous() and pos.is_contiguous()
-    out = torch.empty((B * S, d), device=table.device, dtype=bf16)
+    out = torch.empty((B * S, d), device=table.device, dtype=out_dtype)
     eot = torch.empty(B, device=table.device, dtype=i32)
     ctx, st = _ctx_stream(table)
     L.check(L.load().b200clip_embed_tokens_fwd(ctx, ids.data_ptr(), table.data_ptr(), pos.data_ptr(), out.data_ptr(),
-                                               eot.data_ptr(), B, S, d, V, st), "embed_tokens_fwd")
+                                               _dt(out), eot.data_ptr(), B, S, d, V, st), "embed_tokens_fwd")
     return out, eot
 
 

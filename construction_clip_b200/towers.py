@@ -4,8 +4,10 @@ Mirrors upstream ``clip/model.py`` (``VisionTransformer.forward``, ``CLIP.encode
 ``ResidualAttentionBlock.forward``) -- the code the reference reaches through
 ``model(image, text)`` (CLIP/train.py:161, CLIP/predict.py:46) and ``model.encode_image``
 (CLIP_prefix_caption/parse_coco.py:43) -- but every operator is one hand-written sm_100a kernel
-(see include/b200clip.h).  Activations are token-major ``[B*S, d]`` bf16 (upstream permutes to
-seq-first LND; the maths is layout independent).
+(see include/b200clip.h).  Activations are token-major ``[B*S, d]`` (upstream permutes to seq-first
+LND; the maths is layout independent): the residual stream is fp32 (it accumulates 2 x layers
+branch outputs -- rounding it to bf16 each time alone costs more than the 1e-2 logit tolerance),
+every GEMM / attention operand is bf16, the backward gradient stream is bf16.
 
 ``W`` / ``G`` are dicts ``name -> tensor`` of bf16 weights / fp32 gradient accumulators that use
 upstream's state-dict names relative to the tower prefix.
@@ -60,7 +62,8 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None):
             h1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"])
         qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
         a = O.attn_fwd(qkv, B, S, H, causal)
-        x2 = O.linear_fwd(a, W[p + "attn.out_proj.weight"], W[p + "attn.out_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x)
+        x2 = O.linear_fwd(a, W[p + "attn.out_proj.weight"], W[p + "attn.out_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x,
+                          out_dtype=f32)
         if save:
             h2, mean2, rstd2 = O.layernorm_fwd(x2, W[p + "ln_2.weight"], W[p + "ln_2.bias"], want_stats=True)
             f = torch.empty((x.shape[0], 4 * x.shape[1]), device=x.device, dtype=bf16)
@@ -68,7 +71,8 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None):
             h2 = O.layernorm_fwd(x2, W[p + "ln_2.weight"], W[p + "ln_2.bias"])
             f = None
         g = O.linear_fwd(h2, W[p + "mlp.c_fc.weight"], W[p + "mlp.c_fc.bias"], epilogue=L.EPI_QUICKGELU, preact=f)
-        y = O.linear_fwd(g, W[p + "mlp.c_proj.weight"], W[p + "mlp.c_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x2)
+        y = O.linear_fwd(g, W[p + "mlp.c_proj.weight"], W[p + "mlp.c_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x2,
+                         out_dtype=f32)
         if save:
             saved.blocks.append(BlockSaved(x, mean1, rstd1, h1, qkv, a, x2, mean2, rstd2, h2, f, g))
         x = y
@@ -118,7 +122,7 @@ def _pool_project_bwd(W, G, dfeat, x, row_index, ln_w, ln_b, proj, pooled, mean,
     # dproj[d,E] += pooled^T dfeat ; dpooled = dfeat proj^T
     O.gemm(pooled, dfeat_bf, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, out=G[proj], split_k=0, accumulate=True)
     dpooled = O.gemm(dfeat_bf, W[proj])  # B operand = proj [d, E] read K-major (N = d, K = E)
-    dx = torch.zeros_like(x)
+    dx = torch.zeros(x.shape, device=x.device, dtype=bf16)  # the gradient stream is bf16
     O.layernorm_bwd(dpooled, x, W[ln_w], mean, rstd, G[ln_w], G[ln_b], row_index=row_index, dx=dx)
     return dx
 
@@ -142,7 +146,7 @@ def vision_fwd(W, cfg, image, save: bool):
     pre = torch.empty((B * n, d), device=image.device, dtype=bf16) if save else None
     r = O.layernorm_fwd(patch, W["ln_pre.weight"], W["ln_pre.bias"], rows=B * n, row_index=ridx,
                         neg_row=W["class_embedding"], add=W["positional_embedding"], add_period=n, pre_out=pre,
-                        want_stats=save)
+                        want_stats=save, out_dtype=f32)  # the residual stream is fp32
     x, mean0, rstd0 = r if save else (r, None, None)
     saved = TowerSaved() if save else None
     x = blocks_fwd(W, "transformer.", cfg.vision_layers, x, B, n, H, False, saved)
@@ -174,7 +178,7 @@ def text_fwd(W, cfg, text, save: bool):
     d = cfg.transformer_width
     H = cfg.transformer_heads
     ids = text.to(i32).contiguous()
-    x, eot = O.embed_tokens_fwd(ids, W["token_embedding.weight"], W["positional_embedding"])
+    x, eot = O.embed_tokens_fwd(ids, W["token_embedding.weight"], W["positional_embedding"], out_dtype=f32)
     saved = TowerSaved() if save else None
     x = blocks_fwd(W, "transformer.", cfg.transformer_layers, x, B, S, H, True, saved)
     feat, head = _pool_project_fwd(W, x, eot, "ln_final.weight", "ln_final.bias", "text_projection", save)

@@ -56,7 +56,7 @@ enum {
 enum {
     B200CLIP_EPI_NONE = 0,          /* C = acc (+bias)                                      */
     B200CLIP_EPI_QUICKGELU = 1,     /* C = quickgelu(acc+bias); optional preact = acc+bias  */
-    B200CLIP_EPI_RESIDUAL = 2,      /* C = acc + bias + aux                                 */
+    B200CLIP_EPI_RESIDUAL = 2,      /* C = acc + bias + aux  (aux has C's dtype: bf16 or f32) */
     B200CLIP_EPI_QUICKGELU_BWD = 3  /* C = acc * quickgelu'(aux)                            */
 };
 
@@ -77,7 +77,8 @@ int b200clip_ctx_destroy(b200clip_ctx* ctx);
  *   dgrad    dx = dy W     : A = dy [M,N'] K-major, B = W [N',K'] as MN-major (N := K', K := N')
  *   wgrad    dW = dy^T x   : A = dy [T,N'] MN-major (M := N'), B = x [T,K'] MN-major (N := K'), K := T
  * a_major/b_major: B200CLIP_MAJOR_*.  lda/ldb: row pitch (elements) of the STORED matrix.
- * out_dtype: B200CLIP_DT_BF16 or _F32.  bias: bf16 [N] or NULL.  aux: bf16 [M,N] (ldaux) or NULL.
+ * out_dtype: B200CLIP_DT_BF16 or _F32.  bias: bf16 [N] or NULL.  aux: [M,N] (ldaux) or NULL -- bf16,
+ * except EPI_RESIDUAL with an fp32 C, where aux is fp32 too (the fp32 residual stream).
  * preact: bf16 [M,N] (ldc pitch) or NULL (EPI_QUICKGELU only).
  * scale: optional device fp32 scalar; acc is multiplied by it before bias (NULL = 1).
  * split_k > 1 splits the reduction over `split_k` CTAs per tile and ACCUMULATES into C with
@@ -96,17 +97,20 @@ int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda, int a_majo
  * cat(class_embedding, conv) + positional_embedding + ln_pre):
  *   v = x[src(r),:] + add[(r % add_period),:]   when add != NULL.
  * If pre_out != NULL the pre-normalisation value v is also stored (bf16, ldy pitch).
- * mean/rstd: fp32 [rows] or NULL. */
+ * mean/rstd: fp32 [rows] or NULL.  x_dtype / y_dtype: B200CLIP_DT_BF16 or _F32 -- the residual stream
+ * is kept in fp32 (ln_pre writes fp32; ln_1 / ln_2 / ln_post / ln_final read fp32 and write bf16 GEMM
+ * operands); gamma, beta, neg_row, add, pre_out are always bf16. */
 int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t ldx, const int32_t* row_index,
                            const void* neg_row, const void* add, int64_t add_period, const void* gamma,
                            const void* beta, void* y, int64_t ldy, void* pre_out, float* mean, float* rstd,
-                           int64_t rows, int64_t d, float eps, void* stream);
+                           int64_t rows, int64_t d, float eps, int x_dtype, int y_dtype, void* stream);
 /* dx[dst(r),:] = (dres ? dres[r,:] : 0) + LN'(dy[r,:]) ; dgamma/dbeta fp32 [d] ACCUMULATED (atomics).
- * x is read with the same src(r) mapping as the forward; dx is written at dst(r) = src(r). */
+ * x (x_dtype bf16 or f32) is read with the same src(r) mapping as the forward; dx is written at
+ * dst(r) = src(r).  dy, dres, dx are bf16 (the gradient stream is bf16). */
 int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t lddy, const void* x, int64_t ldx,
                            const int32_t* row_index, const void* gamma, const float* mean, const float* rstd,
                            const void* dres, int64_t lddres, void* dx, int64_t lddx, float* dgamma, float* dbeta,
-                           int64_t rows, int64_t d, void* stream);
+                           int64_t rows, int64_t d, int x_dtype, void* stream);
 
 /* ---- nn.MultiheadAttention(need_weights=False) core: softmax(q k^T / 8 + mask) v, head_dim 64 ----
  * qkv: bf16 [B*S, 3*H*64] (the packed in_proj output: q | k | v, each head-major), out: bf16 [B*S, H*64].
@@ -119,10 +123,11 @@ int b200clip_attn_bwd(b200clip_ctx* ctx, const void* qkv, const void* dout, void
                       int64_t H, int causal, void* stream);
 
 /* ---- token_embedding(text) + positional_embedding  (clip.model.CLIP.encode_text) ---------------
- * ids int32 [B,S]; table bf16 [V,d]; pos bf16 [S,d]; out bf16 [B*S,d]; eot_row int32 [B] receives
+ * ids int32 [B,S]; table bf16 [V,d]; pos bf16 [S,d]; out bf16 or f32 (out_dtype) [B*S,d]; eot_row int32 [B] receives
  * b*S + argmax_s ids[b,s] (first maximum) -- the row upstream pools at. */
 int b200clip_embed_tokens_fwd(b200clip_ctx* ctx, const int32_t* ids, const void* table, const void* pos, void* out,
-                              int32_t* eot_row, int64_t B, int64_t S, int64_t d, int64_t vocab, void* stream);
+                              int out_dtype, int32_t* eot_row, int64_t B, int64_t S, int64_t d, int64_t vocab,
+                              void* stream);
 /* dtable fp32 [V,d] and dpos fp32 [S,d] are ACCUMULATED into (atomics). */
 int b200clip_embed_tokens_bwd(b200clip_ctx* ctx, const int32_t* ids, const void* dout, float* dtable, float* dpos,
                               int64_t B, int64_t S, int64_t d, int64_t vocab, void* stream);

@@ -80,6 +80,9 @@ def test_gemm_epilogues(ops):
     _close(pre, base, 3e-2, 1e-2, "preact")
     _close(got, base * torch.sigmoid(1.702 * base), 3e-2, 1e-2, "quickgelu")
     _close(ops.gemm(a, w, bias=bias, epilogue=L.EPI_RESIDUAL, aux=aux), base + aux.float(), 3e-2, 1e-2, "residual")
+    auxf = torch.randn(M, N, device="cuda")
+    _close(ops.gemm(a, w, bias=bias, epilogue=L.EPI_RESIDUAL, aux=auxf, out_dtype=f32), base + auxf, 1e-3, 1e-3,
+           "residual fp32 stream")
     s = torch.sigmoid(1.702 * aux.float())
     gref = (a.float() @ w.float().t()) * (s * (1 + 1.702 * aux.float() * (1 - s)))
     _close(ops.gemm(a, w, epilogue=L.EPI_QUICKGELU_BWD, aux=aux), gref, 3e-2, 1e-2, "quickgelu_bwd")
@@ -110,6 +113,16 @@ def test_layernorm(ops, rows, d):
     db = torch.zeros(d, device="cuda")
     dx = ops.layernorm_bwd(dy, x, g, mean, rstd, dg, db, dres=dres)
     _close(dx, xr.grad + dres.float(), 3e-2, 2e-2, "ln dx")
+    # fp32 input (the residual stream) / fp32 output variants
+    xf = torch.randn(rows, d, device="cuda") * 2
+    y32, m32, r32 = ops.layernorm_fwd(xf, g, b, want_stats=True)
+    _close(y32, torch.nn.functional.layer_norm(xf, (d,), g.float(), b.float(), 1e-5), 2e-2, 1e-2, "ln fwd f32 in")
+    yf = ops.layernorm_fwd(x, g, b, out_dtype=f32)
+    _close(yf, ref, 1e-4, 1e-4, "ln fwd f32 out")
+    xfr = xf.clone().requires_grad_(True)
+    torch.nn.functional.layer_norm(xfr, (d,), g.float(), b.float(), 1e-5).backward(dy.float())
+    dg2, db2 = torch.zeros(d, device="cuda"), torch.zeros(d, device="cuda")
+    _close(ops.layernorm_bwd(dy, xf, g, m32, r32, dg2, db2), xfr.grad, 3e-2, 2e-2, "ln dx f32 in")
     _close(dg, gr.grad, 1e-2 * math.sqrt(rows), 1e-2, "ln dgamma")
     _close(db, br.grad, 1e-2 * math.sqrt(rows), 1e-2, "ln dbeta")
 
@@ -174,6 +187,8 @@ def test_embed_tokens(ops):
     out, eot = ops.embed_tokens_fwd(ids, table, pos)
     ref = table.float()[ids.long()] + pos.float()[None]
     _close(out, ref.view(-1, d), 1e-3, 1e-2, "embed fwd")
+    out32, _ = ops.embed_tokens_fwd(ids, table, pos, out_dtype=f32)
+    _close(out32, ref.view(-1, d), 1e-7, 1e-6, "embed fwd f32")
     assert torch.equal(eot.long(), torch.arange(B, device="cuda") * S + ids.long().argmax(-1))
     dout = _rand((B * S, d), seed=3)
     dout.view(B, S, d)[0, 40:] = 0
