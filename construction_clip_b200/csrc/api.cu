@@ -1,4 +1,5 @@
 // Context, error reporting and tensor-map construction for libb200clip.
+#include <atomic>
 #include <cstring>
 
 #include "internal.h"
@@ -6,6 +7,9 @@
 namespace b200 {
 
 static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -48,6 +52,8 @@ int init_attention(b200clip_ctx* ctx);
 extern "C" {
 
 int b200clip_abi_version(void) { return B200CLIP_ABI_VERSION; }
+
+uint64_t b200clip_launch_count(void) { return b200::g_launches.load(std::memory_order_relaxed); }
 
 const char* b200clip_last_error(void) { return b200::g_err; }
 

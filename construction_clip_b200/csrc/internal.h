@@ -20,6 +20,10 @@ struct b200clip_ctx {
 };
 
 namespace b200 {
+void count_launch();
+}
+
+namespace b200 {
 
 void set_error(const char* fmt, ...);
 
@@ -48,7 +52,13 @@ void set_error(const char* fmt, ...);
         }                                                         \
     } while (0)
 
-#define B200_LAUNCH_CHECK() B200_CHECK_CUDA(cudaGetLastError())
+// every kernel launch of the library goes through this macro: it counts the launch (bench.py's
+// `gpu_launches`) and surfaces launch-configuration errors
+#define B200_LAUNCH_CHECK()                  \
+    do {                                     \
+        b200::count_launch();                \
+        B200_CHECK_CUDA(cudaGetLastError()); \
+    } while (0)
 
 // 2-D bf16 tensor map, 128-byte swizzle.  dim0 = innermost extent (elements), dim1 = rows,
 // pitch in elements; box = (box0 <= 64, box1 <= 256).

@@ -24,6 +24,7 @@ _p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 SIGNATURES = {
     "b200clip_abi_version": [],
     "b200clip_last_error": [],
+    "b200clip_launch_count": [],
     "b200clip_ctx_create": [C.POINTER(_p), _i],
     "b200clip_ctx_destroy": [_p],
     "b200clip_gemm_bf16": [_p, _p, _l, _i, _p, _l, _i, _p, _l, _i, _p, _p, _l, _p, _p, _l, _l, _l, _i, _i, _i, _p],
@@ -46,7 +47,7 @@ SIGNATURES = {
     "b200clip_clip_loss_bwd": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _p, _p, _p, _p, _l, _p],
     "b200clip_adamw": [_p, _p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _l, _p],
 }
-_RESTYPES = {"b200clip_last_error": C.c_char_p, "b200clip_clip_loss_workspace_bytes": C.c_int64}
+_RESTYPES = {"b200clip_last_error": C.c_char_p, "b200clip_launch_count": C.c_uint64, "b200clip_clip_loss_workspace_bytes": C.c_int64}
 
 _lib = None
 _lock = threading.RLock()
@@ -73,6 +74,10 @@ def load() -> C.CDLL:
                 raise RuntimeError("libb200clip.so ABI version mismatch; rebuild")
             _lib = lib
     return _lib
+
+
+def launch_count() -> int:
+    return int(load().b200clip_launch_count())
 
 
 def last_error() -> str:

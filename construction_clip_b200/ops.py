@@ -38,6 +38,11 @@ def _row_major(t: torch.Tensor, name: str):
 
 
 # ------------------------------------------------------------------------------------------ GEMM
+# bench.py sets this to a list to time every GEMM launch with CUDA events on the launching stream
+# (the roofline of the dominant kernel is measured live, inside the timed region)
+GEMM_PROFILE = None
+
+
 def gemm(a, b, *, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, aux=None, preact=None, scale=None,
          epilogue=L.EPI_NONE, out=None, out_dtype=bf16, split_k=1, accumulate=False):
     """C[M,N] = sum_k A(m,k) B(n,k) (+bias) -> epilogue.  ``a``/``b`` are the STORED matrices:
@@ -60,11 +65,19 @@ def gemm(a, b, *, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, aux=None, pre
     if preact is not None:
         assert _row_major(preact, "preact") == ldc and preact.dtype == bf16
     ctx, st = _ctx_stream(a)
+    prof = GEMM_PROFILE
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     L.check(L.load().b200clip_gemm_bf16(
         ctx, a.data_ptr(), lda, a_major, b.data_ptr(), ldb, b_major, out.data_ptr(), ldc,
         L.DT_F32 if out.dtype == f32 else L.DT_BF16, _ptr(bias), _ptr(aux),
         _row_major(aux, "aux") if aux is not None else 0, _ptr(preact), _ptr(scale), M, N, K, epilogue,
         split_k, 1 if accumulate else 0, st), "gemm_bf16")
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K, (a_major, b_major, M, N, K)))
     return out
 
 

@@ -201,6 +201,42 @@ class ClipTrainer:
                             src = src[:, :math.prod(p.shape[1:])]
                         p.copy_(src.reshape(p.shape))
 
+    # ---------------------------------------------------------------------------- host-fed steps
+    def step_from_host(self, image_host, text_host, next_batch=None):
+        """The step as a data-loader consumer sees it (CLIP/train.py:159 `image.to(device)`):
+        inputs are HOST tensors (pinned for asynchronous copies); the host->device copy of THIS
+        step's batch happens on a copy stream, overlapped with the previous step's compute, and the
+        loss is copied back to a pinned host scalar.  Returns that pinned host tensor (valid after
+        the next synchronisation).  ``next_batch`` optionally prefetches the following batch."""
+        dev = self.device
+        if not hasattr(self, "_copy_stream"):
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staged = None
+            self._loss_host = torch.zeros(64, dtype=f32).pin_memory()
+            self._loss_slot = 0
+        cur = torch.cuda.current_stream(dev)
+
+        def stage(img_h, txt_h):
+            with torch.cuda.stream(self._copy_stream):
+                img_d = img_h.to(dev, non_blocking=True)
+                txt_d = txt_h.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(self._copy_stream)
+            return img_h, img_d, txt_d, ev
+
+        if self._staged is None or self._staged[0] is not image_host:
+            self._staged = stage(image_host, text_host)
+        _, img_d, txt_d, ev = self._staged
+        cur.wait_event(ev)
+        img_d.record_stream(cur)
+        txt_d.record_stream(cur)
+        self._staged = stage(*next_batch) if next_batch is not None else None
+        loss = self.step(img_d, txt_d)
+        slot = self._loss_host[self._loss_slot:self._loss_slot + 1]
+        self._loss_slot = (self._loss_slot + 1) % 64
+        slot.copy_(loss.reshape(1), non_blocking=True)
+        return slot
+
     def step(self, image, text):
         """One optimisation step on this rank's slice (image [Bl,3,R,R], text [Bl,77]) of the
         global batch; returns the global mean loss as a device tensor (no host sync)."""

@@ -66,6 +66,8 @@ typedef struct b200clip_ctx b200clip_ctx;
 
 int b200clip_abi_version(void);
 const char* b200clip_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (monotonic). */
+uint64_t b200clip_launch_count(void);
 /* Creates the per-device context (resolves the driver's tensor-map encoder, sets kernel
  * attributes).  Fails with B200CLIP_ERR_DEVICE when `device` is not compute capability 10.x. */
 int b200clip_ctx_create(b200clip_ctx** out, int device);
