@@ -6,10 +6,12 @@
 // `x @ visual.proj`, `x @ text_projection` and their autograd dgrad / wgrad
 // (reference call sites: CLIP/train.py:161 forward, CLIP/train.py:168 backward).
 //
-// One persistent CTA per SM, 6 warps:
+// One persistent CTA per SM, 10 warps:
 //   warp 0     TMA producer (one elected lane)
 //   warp 1     TMEM allocator + MMA issuer (one elected lane)
-//   warps 2-5  epilogue (each owns one 32-lane TMEM quadrant = 32 rows of the 128-row tile)
+//   warps 2-9  epilogue: warp w drains TMEM lane quadrant w%4 (32 rows of the 128-row tile) for one
+//              half of the tile's columns, transposing through shared memory so that every global
+//              access (aux load, C store) is a full 128-byte row segment
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty pair (MMA <-> epilogue).
 #include "common.cuh"
 #include "internal.h"
@@ -19,8 +21,10 @@ namespace b200 {
 constexpr int BM = 128;           // tile rows  (UMMA M, cta_group::1)
 constexpr int BK = 64;            // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;        // fixed for 16-bit inputs
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;       // two warps per TMEM lane quadrant, each takes half of the tile's columns
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kStageBytesA = BM * BK * 2;  // 16 KB
+constexpr int kEpiStageBytes = 32 * 128;   // per-warp staging: 32 rows x 128 B, XOR-swizzled
 
 template <int BN>
 struct GemmCfg {
@@ -28,7 +32,7 @@ struct GemmCfg {
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
     static constexpr int kStages = (BN == 256) ? 4 : 6;
     static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024;  // + alignment slack
+    static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024;  // + align slack
 };
 
 struct GemmParams {
@@ -121,29 +125,141 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32
     }
 }
 
-__device__ __forceinline__ void epilogue_dispatch(const GemmParams& p, const uint32_t (&acc)[32], int row, int col0,
-                                                  float scale) {
-    if (p.out_f32) {
-        if (p.epilogue == B200CLIP_EPI_RESIDUAL)
-            epilogue_chunk<B200CLIP_EPI_RESIDUAL, true, false>(p, acc, row, col0, scale);
-        else if (p.atomic_out)
-            epilogue_chunk<B200CLIP_EPI_NONE, true, true>(p, acc, row, col0, scale);
-        else
-            epilogue_chunk<B200CLIP_EPI_NONE, true, false>(p, acc, row, col0, scale);
-    } else {
-        switch (p.epilogue) {
-            case B200CLIP_EPI_QUICKGELU:
-                epilogue_chunk<B200CLIP_EPI_QUICKGELU, false, false>(p, acc, row, col0, scale);
-                break;
-            case B200CLIP_EPI_RESIDUAL:
-                epilogue_chunk<B200CLIP_EPI_RESIDUAL, false, false>(p, acc, row, col0, scale);
-                break;
-            case B200CLIP_EPI_QUICKGELU_BWD:
-                epilogue_chunk<B200CLIP_EPI_QUICKGELU_BWD, false, false>(p, acc, row, col0, scale);
-                break;
-            default:
-                epilogue_chunk<B200CLIP_EPI_NONE, false, false>(p, acc, row, col0, scale);
-                break;
+// ------------------------------------------------------------------------------------------------
+// Coalesced epilogue.  TMEM hands each thread one accumulator ROW; writing rows straight to global
+// memory makes every warp-level store touch 32 different lines.  Instead each warp transposes
+// through a private 4 KB shared-memory staging tile (32 rows x 128 B, 16-byte chunks XOR-swizzled
+// with the row so both access patterns are bank-conflict free):
+//   row layout       : thread = row, 8 chunks of 16 B                      (TMEM side, the maths)
+//   coalesced layout : 8 lanes cover one 128-byte row segment, 4 rows/instr (global side)
+// aux (residual / saved pre-activation) is fetched with coalesced loads through the same tile.
+__device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
+    return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+template <int EPI, bool OUT_F32>
+__device__ __forceinline__ void epilogue_staged(const GemmParams& p, uint32_t taddr, int m_base, int n_base,
+                                                int ncols, float scale, uint8_t* stg, int lane) {
+    constexpr int EPC = OUT_F32 ? 4 : 8;   // elements per 16-byte chunk of C (and of aux: same dtype as C,
+    constexpr int CW = 8 * EPC;            //  except QUICKGELU_BWD whose aux and C are both bf16)
+    constexpr bool HAS_AUX = (EPI == B200CLIP_EPI_RESIDUAL || EPI == B200CLIP_EPI_QUICKGELU_BWD);
+    constexpr int ESZ = OUT_F32 ? 4 : 2;
+    const int rrow = lane >> 3, rch = lane & 7;
+    uint8_t* Cb = reinterpret_cast<uint8_t*>(p.C);
+    const uint8_t* Ab = reinterpret_cast<const uint8_t*>(p.aux);
+#pragma unroll 1
+    for (int j = 0; j < ncols / CW; ++j) {
+        const int col0 = n_base + j * CW;
+        if (col0 >= p.N) break;  // warp-uniform
+        uint32_t acc[CW];
+        {
+            uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&acc[0]);
+            tmem_ld_32x32(taddr + j * CW, lo);
+            if constexpr (CW == 64) {
+                uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&acc[32]);
+                tmem_ld_32x32(taddr + j * CW + 32, hi);
+            }
+        }
+        uint4 auxv[8];
+        if constexpr (HAS_AUX) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = 4 * i + rrow;
+                const int grow = m_base + row, col = col0 + rch * EPC;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (grow < p.M && col < p.N)
+                    v = *reinterpret_cast<const uint4*>(Ab + (static_cast<int64_t>(grow) * p.ldaux + col) * ESZ);
+                *reinterpret_cast<uint4*>(stg + stage_off(row, rch)) = v;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 8; ++c) auxv[c] = *reinterpret_cast<const uint4*>(stg + stage_off(lane, c));
+            __syncwarp();
+        }
+        tmem_ld_wait();
+        // ---- the maths, one 16-byte output chunk at a time (row layout)
+        [[maybe_unused]] uint4 pre[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const int col = col0 + c * EPC;
+            float x[EPC];
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) x[e] = __uint_as_float(acc[c * EPC + e]) * scale;
+            if (p.bias != nullptr && col < p.N) {
+                if constexpr (EPC == 8) {
+                    const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
+                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const float2 f = unpack_bf16(bw[i]);
+                        x[2 * i] += f.x;
+                        x[2 * i + 1] += f.y;
+                    }
+                } else {
+                    const uint2 b = __ldg(reinterpret_cast<const uint2*>(p.bias + col));
+                    const float2 f0 = unpack_bf16(b.x), f1 = unpack_bf16(b.y);
+                    x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
+                }
+            }
+            if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
+                if (p.preact != nullptr)
+                    pre[c] = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
+                                        pack_bf16(x[6], x[7]));
+#pragma unroll
+                for (int e = 0; e < EPC; ++e) x[e] = quick_gelu(x[e]);
+            } else if constexpr (EPI == B200CLIP_EPI_RESIDUAL && OUT_F32) {
+                x[0] += __uint_as_float(auxv[c].x);
+                x[1] += __uint_as_float(auxv[c].y);
+                x[2] += __uint_as_float(auxv[c].z);
+                x[3] += __uint_as_float(auxv[c].w);
+            } else if constexpr (HAS_AUX) {
+                const uint32_t aw[4] = {auxv[c].x, auxv[c].y, auxv[c].z, auxv[c].w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float2 f = unpack_bf16(aw[i]);
+                    if constexpr (EPI == B200CLIP_EPI_RESIDUAL) {
+                        x[2 * i] += f.x;
+                        x[2 * i + 1] += f.y;
+                    } else {
+                        x[2 * i] *= quick_gelu_grad(f.x);
+                        x[2 * i + 1] *= quick_gelu_grad(f.y);
+                    }
+                }
+            }
+            uint4 o;
+            if constexpr (OUT_F32) {
+                o = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
+            } else {
+                o = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
+            }
+            *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) = o;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int row = 4 * i + rrow;
+            const int grow = m_base + row, col = col0 + rch * EPC;
+            const uint4 v = *reinterpret_cast<const uint4*>(stg + stage_off(row, rch));
+            if (grow < p.M && col < p.N)
+                *reinterpret_cast<uint4*>(Cb + (static_cast<int64_t>(grow) * p.ldc + col) * ESZ) = v;
+        }
+        __syncwarp();
+        if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
+            if (p.preact != nullptr) {  // second output: the pre-activation (saved for the backward)
+#pragma unroll
+                for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) = pre[c];
+                __syncwarp();
+                uint8_t* Pb = reinterpret_cast<uint8_t*>(p.preact);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int row = 4 * i + rrow;
+                    const int grow = m_base + row, col = col0 + rch * EPC;
+                    const uint4 v = *reinterpret_cast<const uint4*>(stg + stage_off(row, rch));
+                    if (grow < p.M && col < p.N)
+                        *reinterpret_cast<uint4*>(Pb + (static_cast<int64_t>(grow) * p.ldc + col) * ESZ) = v;
+                }
+                __syncwarp();
+            }
         }
     }
 }
@@ -177,7 +293,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], 4);  // one arrive per epilogue warp
+            mbar_init(&tmem_empty_bar[s], kEpiWarps);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -275,26 +391,54 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else {
         // ===================================== epilogue warps ===================================
-        const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+        const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+        const int half = (warp - 2) >> 2;    // which half of the tile's columns this warp drains
+        uint8_t* stg = smem + kStages * Cfg::kStageBytes + (warp - 2) * kEpiStageBytes;
         int as = 0;
         uint32_t aphase = 0;
         const float scale = (p.scale != nullptr) ? __ldg(p.scale) : 1.0f;
         for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
             const int tile = w / p.split_k;
             const int m0 = (tile / p.num_n_tiles) * BM;
-            const int n0 = (tile % p.num_n_tiles) * BN;
+            const int n0 = (tile % p.num_n_tiles) * BN + half * (BN / 2);
             mbar_wait(&tmem_full_bar[as], aphase);
+            __syncwarp();
             tc_fence_after();
-            const int row = m0 + quad * 32 + lane;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(as * BN);
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                                   static_cast<uint32_t>(as * BN + half * (BN / 2));
+            const int m_base = m0 + quad * 32;
+            if (p.atomic_out) {
+                // split-K / accumulate: fp32 atomics straight from the row layout
+                const int row = m_base + lane;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                const int col0 = n0 + c * 32;
-                if (col0 >= p.N) break;  // warp-uniform
-                uint32_t acc[32];
-                tmem_ld_32x32(taddr + c * 32, acc);
-                tmem_ld_wait();
-                epilogue_dispatch(p, acc, row, col0, scale);
+                for (int c = 0; c < BN / 64; ++c) {
+                    const int col0 = n0 + c * 32;
+                    if (col0 >= p.N) break;  // warp-uniform
+                    uint32_t acc[32];
+                    tmem_ld_32x32(taddr + c * 32, acc);
+                    tmem_ld_wait();
+                    epilogue_chunk<B200CLIP_EPI_NONE, true, true>(p, acc, row, col0, scale);
+                }
+            } else if (p.out_f32) {
+                if (p.epilogue == B200CLIP_EPI_RESIDUAL)
+                    epilogue_staged<B200CLIP_EPI_RESIDUAL, true>(p, taddr, m_base, n0, BN / 2, scale, stg, lane);
+                else
+                    epilogue_staged<B200CLIP_EPI_NONE, true>(p, taddr, m_base, n0, BN / 2, scale, stg, lane);
+            } else {
+                switch (p.epilogue) {
+                    case B200CLIP_EPI_QUICKGELU:
+                        epilogue_staged<B200CLIP_EPI_QUICKGELU, false>(p, taddr, m_base, n0, BN / 2, scale, stg, lane);
+                        break;
+                    case B200CLIP_EPI_RESIDUAL:
+                        epilogue_staged<B200CLIP_EPI_RESIDUAL, false>(p, taddr, m_base, n0, BN / 2, scale, stg, lane);
+                        break;
+                    case B200CLIP_EPI_QUICKGELU_BWD:
+                        epilogue_staged<B200CLIP_EPI_QUICKGELU_BWD, false>(p, taddr, m_base, n0, BN / 2, scale, stg, lane);
+                        break;
+                    default:
+                        epilogue_staged<B200CLIP_EPI_NONE, false>(p, taddr, m_base, n0, BN / 2, scale, stg, lane);
+                        break;
+                }
             }
             tc_fence_before();
             __syncwarp();
