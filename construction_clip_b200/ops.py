@@ -132,22 +132,24 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, *, row_index=None, dr
 
 
 # ------------------------------------------------------------------------------------- attention
-def attn_fwd(qkv, B, S, H, causal, out=None):
+def attn_fwd(qkv, B, S, H, causal, out=None, want_lse=False):
     assert qkv.dtype == bf16 and qkv.is_contiguous() and qkv.shape == (B * S, 3 * H * 64)
     if out is None:
         out = torch.empty((B * S, H * 64), device=qkv.device, dtype=bf16)
+    lse = torch.empty(B * H * S, device=qkv.device, dtype=f32) if want_lse else None
     ctx, st = _ctx_stream(qkv)
-    L.check(L.load().b200clip_attn_fwd(ctx, qkv.data_ptr(), out.data_ptr(), B, S, H, 1 if causal else 0, st), "attn_fwd")
-    return out
+    L.check(L.load().b200clip_attn_fwd(ctx, qkv.data_ptr(), out.data_ptr(), _ptr(lse), B, S, H, 1 if causal else 0, st),
+            "attn_fwd")
+    return (out, lse) if want_lse else out
 
 
-def attn_bwd(qkv, dout, B, S, H, causal, dqkv=None):
-    assert qkv.is_contiguous() and dout.is_contiguous() and dout.shape == (B * S, H * 64)
+def attn_bwd(qkv, out, lse, dout, B, S, H, causal, dqkv=None):
+    assert qkv.is_contiguous() and dout.is_contiguous() and out.is_contiguous() and dout.shape == (B * S, H * 64)
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
     ctx, st = _ctx_stream(qkv)
-    L.check(L.load().b200clip_attn_bwd(ctx, qkv.data_ptr(), dout.data_ptr(), dqkv.data_ptr(), B, S, H,
-                                       1 if causal else 0, st), "attn_bwd")
+    L.check(L.load().b200clip_attn_bwd(ctx, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), dout.data_ptr(),
+                                       dqkv.data_ptr(), B, S, H, 1 if causal else 0, st), "attn_bwd")
     return dqkv
 
 

@@ -32,6 +32,7 @@ class BlockSaved:
     h1: torch.Tensor = None
     qkv: torch.Tensor = None
     a: torch.Tensor = None
+    lse: torch.Tensor = None
     x2: torch.Tensor = None
     mean2: torch.Tensor = None
     rstd2: torch.Tensor = None
@@ -61,7 +62,10 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None):
         else:
             h1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"])
         qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
-        a = O.attn_fwd(qkv, B, S, H, causal)
+        if save:
+            a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True)
+        else:
+            a, lse = O.attn_fwd(qkv, B, S, H, causal), None
         x2 = O.linear_fwd(a, W[p + "attn.out_proj.weight"], W[p + "attn.out_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x,
                           out_dtype=f32)
         if save:
@@ -74,7 +78,7 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None):
         y = O.linear_fwd(g, W[p + "mlp.c_proj.weight"], W[p + "mlp.c_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x2,
                          out_dtype=f32)
         if save:
-            saved.blocks.append(BlockSaved(x, mean1, rstd1, h1, qkv, a, x2, mean2, rstd2, h2, f, g))
+            saved.blocks.append(BlockSaved(x, mean1, rstd1, h1, qkv, a, lse, x2, mean2, rstd2, h2, f, g))
         x = y
     return x
 
@@ -96,7 +100,7 @@ def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved):
         O.colsum(dx2, G[p + "attn.out_proj.bias"])
         O.linear_wgrad(dx2, s.a, G[p + "attn.out_proj.weight"])
         da = O.linear_dgrad(dx2, W[p + "attn.out_proj.weight"])
-        dqkv = O.attn_bwd(s.qkv, da, B, S, H, causal)
+        dqkv = O.attn_bwd(s.qkv, s.a, s.lse, da, B, S, H, causal)
         O.colsum(dqkv, G[p + "attn.in_proj_bias"])
         O.linear_wgrad(dqkv, s.h1, G[p + "attn.in_proj_weight"])
         dh1 = O.linear_dgrad(dqkv, W[p + "attn.in_proj_weight"])

@@ -118,11 +118,13 @@ int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t lddy, cons
  * qkv: bf16 [B*S, 3*H*64] (the packed in_proj output: q | k | v, each head-major), out: bf16 [B*S, H*64].
  * causal != 0 applies upstream's build_attention_mask (-inf strictly above the diagonal; padding is
  * NOT masked).  S <= 128 (single tile) in this version. */
-int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, int64_t B, int64_t S, int64_t H, int causal,
-                      void* stream);
-/* dqkv: bf16 [B*S, 3*H*64]; probabilities are recomputed from qkv (nothing saved by the forward). */
-int b200clip_attn_bwd(b200clip_ctx* ctx, const void* qkv, const void* dout, void* dqkv, int64_t B, int64_t S,
-                      int64_t H, int causal, void* stream);
+int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H,
+                      int causal, void* stream);
+/* dqkv: bf16 [B*S, 3*H*64].  `out` and `lse` are the forward's results (lse: fp32 [B*H*S], the row
+ * log-sum-exp in the log2 domain; pass a buffer to b200clip_attn_fwd when a backward will follow,
+ * NULL otherwise); probabilities are recomputed from q,k and lse. */
+int b200clip_attn_bwd(b200clip_ctx* ctx, const void* qkv, const void* out, const float* lse, const void* dout,
+                      void* dqkv, int64_t B, int64_t S, int64_t H, int causal, void* stream);
 
 /* ---- token_embedding(text) + positional_embedding  (clip.model.CLIP.encode_text) ---------------
  * ids int32 [B,S]; table bf16 [V,d]; pos bf16 [S,d]; out bf16 or f32 (out_dtype) [B*S,d]; eot_row int32 [B] receives

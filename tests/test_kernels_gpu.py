@@ -164,13 +164,13 @@ def _attn_ref(qkv, B, S, H, causal):
                                           (1, 128, 2, True), (40, 50, 12, False), (33, 77, 8, True), (2, 7, 1, True)])
 def test_attention_fwd_bwd(ops, B, S, H, causal):
     qkv = _rand((B * S, 3 * H * 64), 1.5, seed=S)
-    out = ops.attn_fwd(qkv, B, S, H, causal)
+    out, lse = ops.attn_fwd(qkv, B, S, H, causal, want_lse=True)
     qr = qkv.float().requires_grad_(True)
     ref = _attn_ref(qr, B, S, H, causal)
     _close(out, ref, 2e-2, 2e-2, "attn fwd")
     dout = _rand((B * S, H * 64), seed=S + 1)
     ref.backward(dout.float())
-    dqkv = ops.attn_bwd(qkv, dout, B, S, H, causal)
+    dqkv = ops.attn_bwd(qkv, out, lse, dout, B, S, H, causal)
     _close(dqkv, qr.grad, 4e-2, 4e-2, "attn bwd")
 
 

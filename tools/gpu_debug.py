@@ -78,7 +78,7 @@ for s in steps:
         for (B, S, H, causal) in [(2, 50, 12, False), (3, 77, 8, True)]:
             qkv = torch.randn(B * S, 3 * H * 64, device="cuda").to(bf16)
             log("   launching attn fwd", B, S, H, causal)
-            o = O.attn_fwd(qkv, B, S, H, causal)
+            o, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True)
             sync("attn fwd")
             q, k, v = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
             sc = q @ k.transpose(-1, -2) / 8.0
@@ -87,7 +87,7 @@ for s in steps:
             ref = (torch.softmax(sc, -1) @ v).permute(0, 2, 1, 3).reshape(B * S, H * 64)
             log("   attn fwd max err", (o.float() - ref).abs().max().item())
             do = torch.randn(B * S, H * 64, device="cuda").to(bf16)
-            dq = O.attn_bwd(qkv, do, B, S, H, causal)
+            dq = O.attn_bwd(qkv, o, lse, do, B, S, H, causal)
             sync("attn bwd")
             log("   attn bwd absmax", dq.float().abs().max().item())
 log("done")
