@@ -1,0 +1,57 @@
+"""Times every GEMM shape of the ViT-B/32 train step (per-GPU batch 1024) in isolation."""
+import sys
+import torch
+sys.path.insert(0, ".")
+from construction_clip_b200 import lib as L, ops as O
+
+bf16, f32 = torch.bfloat16, torch.float32
+dev = "cuda"
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+
+
+def timeit(fn, iters=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+rows = []
+for tower, M, d in (("vis", B * 50, 768), ("txt", B * 77, 512)):
+    x = torch.randn(M, d, device=dev).to(bf16)
+    x4 = torch.randn(M, 4 * d, device=dev).to(bf16)
+    x3 = torch.randn(M, 3 * d, device=dev).to(bf16)
+    xf = torch.randn(M, d, device=dev)
+    for name, N, K in (("qkv", 3 * d, d), ("out", d, d), ("fc", 4 * d, d), ("proj", d, 4 * d)):
+        w = torch.randn(N, K, device=dev).to(bf16)
+        bias = torch.randn(N, device=dev).to(bf16)
+        a = x if K == d else x4
+        dy = {d: x, 3 * d: x3, 4 * d: x4}[N]
+        fl = 2.0 * M * N * K
+        if name == "fc":
+            pre = torch.empty(M, N, device=dev, dtype=bf16)
+            t = timeit(lambda: O.gemm(a, w, bias=bias, epilogue=L.EPI_QUICKGELU, preact=pre))
+        elif name in ("out", "proj"):
+            t = timeit(lambda: O.gemm(a, w, bias=bias, epilogue=L.EPI_RESIDUAL, aux=xf, out_dtype=f32))
+        else:
+            t = timeit(lambda: O.gemm(a, w, bias=bias))
+        rows.append((tower, name, "fwd", M, N, K, t, fl / t / 1e9))
+        if name == "proj":
+            t = timeit(lambda: O.gemm(dy, w, b_major=L.MAJOR_MN, epilogue=L.EPI_QUICKGELU_BWD, aux=x4))
+        else:
+            t = timeit(lambda: O.gemm(dy, w, b_major=L.MAJOR_MN))
+        rows.append((tower, name, "dgrad", M, K, N, t, fl / t / 1e9))
+        g = torch.zeros(N, K, device=dev)
+        t = timeit(lambda: O.gemm(dy, a, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, out=g, split_k=0, accumulate=True))
+        rows.append((tower, name, "wgrad", N, K, M, t, fl / t / 1e9))
+tot_t = sum(r[6] for r in rows)
+tot_f = sum(r[7] * r[6] for r in rows)
+for r in rows:
+    print(f"{r[0]:4s} {r[1]:5s} {r[2]:6s} M={r[3]:6d} N={r[4]:5d} K={r[5]:6d}  {r[6]*1e3:8.1f} us  {r[7]:7.1f} TFLOP/s")
+print(f"per-layer total {tot_t*1e3:.1f} us  avg {tot_f/tot_t:.1f} TFLOP/s ; x12 layers = {tot_t*12:.2f} ms")
