@@ -49,219 +49,135 @@ struct GemmParams {
 };
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue for one 32-column chunk held by one thread (one output row).
-template <int EPI, bool OUT_F32, bool ATOMIC>
-__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, const uint32_t (&acc)[32], int row, int col0,
-                                               float scale) {
-    if (row >= p.M) return;
-    const int ncols = min(32, p.N - col0);  // N % 8 == 0 guaranteed by the host
-#pragma unroll
-    for (int v = 0; v < 4; ++v) {  // 4 vectors of 8 columns
-        if (v * 8 >= ncols) break;
-        const int col = col0 + v * 8;
-        float x[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) x[i] = __uint_as_float(acc[v * 8 + i]) * scale;
-        if (p.bias != nullptr) {
-            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
-            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16(bw[i]);
-                x[2 * i] += f.x;
-                x[2 * i + 1] += f.y;
-            }
-        }
-        if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
-            if (p.preact != nullptr) {
-                uint4 o;
-                o.x = pack_bf16(x[0], x[1]);
-                o.y = pack_bf16(x[2], x[3]);
-                o.z = pack_bf16(x[4], x[5]);
-                o.w = pack_bf16(x[6], x[7]);
-                *reinterpret_cast<uint4*>(p.preact + static_cast<int64_t>(row) * p.ldc + col) = o;
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) x[i] = quick_gelu(x[i]);
-        } else if constexpr (EPI == B200CLIP_EPI_RESIDUAL && OUT_F32) {
-            // fp32 residual stream: aux and C are fp32
-            const float* ap = reinterpret_cast<const float*>(p.aux) + static_cast<int64_t>(row) * p.ldaux + col;
-            const float4 a0 = *reinterpret_cast<const float4*>(ap);
-            const float4 a1 = *reinterpret_cast<const float4*>(ap + 4);
-            x[0] += a0.x; x[1] += a0.y; x[2] += a0.z; x[3] += a0.w;
-            x[4] += a1.x; x[5] += a1.y; x[6] += a1.z; x[7] += a1.w;
-        } else if constexpr (EPI == B200CLIP_EPI_RESIDUAL || EPI == B200CLIP_EPI_QUICKGELU_BWD) {
-            const uint4 a = *reinterpret_cast<const uint4*>(p.aux + static_cast<int64_t>(row) * p.ldaux + col);
-            const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float2 f = unpack_bf16(aw[i]);
-                if constexpr (EPI == B200CLIP_EPI_RESIDUAL) {
-                    x[2 * i] += f.x;
-                    x[2 * i + 1] += f.y;
-                } else {
-                    x[2 * i] *= quick_gelu_grad(f.x);
-                    x[2 * i + 1] *= quick_gelu_grad(f.y);
-                }
-            }
-        }
-        if constexpr (OUT_F32) {
-            float* dst = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(row) * p.ldc + col;
-            if constexpr (ATOMIC) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) atomicAdd(dst + i, x[i]);
-            } else {
-                *reinterpret_cast<float4*>(dst) = make_float4(x[0], x[1], x[2], x[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(x[4], x[5], x[6], x[7]);
-            }
-        } else {
-            uint4 o;
-            o.x = pack_bf16(x[0], x[1]);
-            o.y = pack_bf16(x[2], x[3]);
-            o.z = pack_bf16(x[4], x[5]);
-            o.w = pack_bf16(x[6], x[7]);
-            *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(row) * p.ldc + col) = o;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Coalesced epilogue.  TMEM hands each thread one accumulator ROW; writing rows straight to global
-// memory makes every warp-level store touch 32 different lines.  Instead each warp transposes
-// through a private 4 KB shared-memory staging tile (32 rows x 128 B, 16-byte chunks XOR-swizzled
-// with the row so both access patterns are bank-conflict free):
-//   row layout       : thread = row, 8 chunks of 16 B                      (TMEM side, the maths)
-//   coalesced layout : 8 lanes cover one 128-byte row segment, 4 rows/instr (global side)
-// aux (residual / saved pre-activation) is fetched with coalesced loads through the same tile.
+// Epilogue.  TMEM hands each thread one accumulator ROW (lane = row); writing rows straight to
+// global memory would make every warp-level access touch 32 different lines.  Each epilogue warp
+// therefore transposes 32 x 32 fp32 accumulator blocks through a private 4 KB shared-memory tile
+// (16-byte chunks XOR-swizzled with the row: both access patterns are bank-conflict free) and does
+// ALL the epilogue maths in the coalesced layout, where a lane owns 4 consecutive columns of 8
+// different rows: bias is loaded once per block into registers, aux (fp32 residual stream or the
+// saved bf16 pre-activation) is read with coalesced loads issued before the transpose, and the
+// result leaves as 8/16-byte stores that cover whole 32-byte sectors.
+// The tcgen05.ld of a block is in flight while its aux / bias loads are issued.
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
     return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
-template <int EPI, bool OUT_F32>
-__device__ __forceinline__ void epilogue_staged(const GemmParams& p, uint32_t taddr, int m_base, int n_base,
-                                                int ncols, float scale, uint8_t* stg, int lane) {
-    constexpr int EPC = OUT_F32 ? 4 : 8;   // elements per 16-byte chunk of C (and of aux: same dtype as C,
-    constexpr int CW = 8 * EPC;            //  except QUICKGELU_BWD whose aux and C are both bf16)
-    constexpr bool HAS_AUX = (EPI == B200CLIP_EPI_RESIDUAL || EPI == B200CLIP_EPI_QUICKGELU_BWD);
-    constexpr int ESZ = OUT_F32 ? 4 : 2;
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// out = 0.5 x (1 + tanh(0.851 x)) = x * sigmoid(1.702 x)                       (4 instructions)
+__device__ __forceinline__ float qgelu_fast(float x) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.851f * x));
+    const float h = 0.5f * x;
+    return fmaf(h, t, h);
+}
+// acc * d/dx[x sigmoid(1.702x)] = 0.5 acc (1 + t + u (1 - t^2)), u = 0.851 x, t = tanh(u)   (6 instr.)
+__device__ __forceinline__ float qgelu_bwd_fast(float acc, float x) {
+    const float u = 0.851f * x;
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    const float a = fmaf(-t, t, 1.0f);
+    const float c = fmaf(u, a, t);
+    const float h = 0.5f * acc;
+    return fmaf(h, c, h);
+}
+
+template <int EPI, bool OUT_F32, bool ATOMIC>
+__device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t taddr, int m_base, int col0, float scale,
+                                               uint8_t* stg, int lane) {
+    uint32_t acc[32];
+    tmem_ld_32x32(taddr, acc);  // asynchronous until tcgen05.wait::ld below
+    constexpr bool AUX_F32 = (EPI == B200CLIP_EPI_RESIDUAL) && OUT_F32;
+    constexpr bool AUX_BF16 = (EPI == B200CLIP_EPI_QUICKGELU_BWD) || (EPI == B200CLIP_EPI_RESIDUAL && !OUT_F32);
     const int rrow = lane >> 3, rch = lane & 7;
-    uint8_t* Cb = reinterpret_cast<uint8_t*>(p.C);
-    const uint8_t* Ab = reinterpret_cast<const uint8_t*>(p.aux);
-#pragma unroll 1
-    for (int j = 0; j < ncols / CW; ++j) {
-        const int col0 = n_base + j * CW;
-        if (col0 >= p.N) break;  // warp-uniform
-        uint32_t acc[CW];
-        {
-            uint32_t (&lo)[32] = *reinterpret_cast<uint32_t (*)[32]>(&acc[0]);
-            tmem_ld_32x32(taddr + j * CW, lo);
-            if constexpr (CW == 64) {
-                uint32_t (&hi)[32] = *reinterpret_cast<uint32_t (*)[32]>(&acc[32]);
-                tmem_ld_32x32(taddr + j * CW + 32, hi);
-            }
-        }
-        uint4 auxv[8];
-        if constexpr (HAS_AUX) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int row = 4 * i + rrow;
-                const int grow = m_base + row, col = col0 + rch * EPC;
-                uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                if (grow < p.M && col < p.N)
-                    v = *reinterpret_cast<const uint4*>(Ab + (static_cast<int64_t>(grow) * p.ldaux + col) * ESZ);
-                *reinterpret_cast<uint4*>(stg + stage_off(row, rch)) = v;
-            }
-            __syncwarp();
-#pragma unroll
-            for (int c = 0; c < 8; ++c) auxv[c] = *reinterpret_cast<const uint4*>(stg + stage_off(lane, c));
-            __syncwarp();
-        }
-        tmem_ld_wait();
-        // ---- the maths, one 16-byte output chunk at a time (row layout)
-        [[maybe_unused]] uint4 pre[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            const int col = col0 + c * EPC;
-            float x[EPC];
-#pragma unroll
-            for (int e = 0; e < EPC; ++e) x[e] = __uint_as_float(acc[c * EPC + e]) * scale;
-            if (p.bias != nullptr && col < p.N) {
-                if constexpr (EPC == 8) {
-                    const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + col));
-                    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float2 f = unpack_bf16(bw[i]);
-                        x[2 * i] += f.x;
-                        x[2 * i + 1] += f.y;
-                    }
-                } else {
-                    const uint2 b = __ldg(reinterpret_cast<const uint2*>(p.bias + col));
-                    const float2 f0 = unpack_bf16(b.x), f1 = unpack_bf16(b.y);
-                    x[0] += f0.x; x[1] += f0.y; x[2] += f1.x; x[3] += f1.y;
-                }
-            }
-            if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
-                if (p.preact != nullptr)
-                    pre[c] = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]),
-                                        pack_bf16(x[6], x[7]));
-#pragma unroll
-                for (int e = 0; e < EPC; ++e) x[e] = quick_gelu(x[e]);
-            } else if constexpr (EPI == B200CLIP_EPI_RESIDUAL && OUT_F32) {
-                x[0] += __uint_as_float(auxv[c].x);
-                x[1] += __uint_as_float(auxv[c].y);
-                x[2] += __uint_as_float(auxv[c].z);
-                x[3] += __uint_as_float(auxv[c].w);
-            } else if constexpr (HAS_AUX) {
-                const uint32_t aw[4] = {auxv[c].x, auxv[c].y, auxv[c].z, auxv[c].w};
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const float2 f = unpack_bf16(aw[i]);
-                    if constexpr (EPI == B200CLIP_EPI_RESIDUAL) {
-                        x[2 * i] += f.x;
-                        x[2 * i + 1] += f.y;
-                    } else {
-                        x[2 * i] *= quick_gelu_grad(f.x);
-                        x[2 * i + 1] *= quick_gelu_grad(f.y);
-                    }
-                }
-            }
-            uint4 o;
-            if constexpr (OUT_F32) {
-                o = make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), __float_as_uint(x[3]));
-            } else {
-                o = make_uint4(pack_bf16(x[0], x[1]), pack_bf16(x[2], x[3]), pack_bf16(x[4], x[5]), pack_bf16(x[6], x[7]));
-            }
-            *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) = o;
-        }
-        __syncwarp();
+    const int col = col0 + rch * 4;
+    const bool col_ok = col < p.N;  // N % 8 == 0 and col % 4 == 0: the 4 columns are all in or all out
+    // ---- loads that do not depend on the transpose: aux (coalesced) and bias
+    [[maybe_unused]] uint4 auxf[8];
+    [[maybe_unused]] uint2 auxh[8];
+    if constexpr (AUX_F32) {
+        const float* ap = reinterpret_cast<const float*>(p.aux);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int row = 4 * i + rrow;
-            const int grow = m_base + row, col = col0 + rch * EPC;
-            const uint4 v = *reinterpret_cast<const uint4*>(stg + stage_off(row, rch));
-            if (grow < p.M && col < p.N)
-                *reinterpret_cast<uint4*>(Cb + (static_cast<int64_t>(grow) * p.ldc + col) * ESZ) = v;
+            const int grow = m_base + 4 * i + rrow;
+            auxf[i] = (col_ok && grow < p.M) ? *reinterpret_cast<const uint4*>(ap + static_cast<int64_t>(grow) * p.ldaux + col)
+                                             : make_uint4(0u, 0u, 0u, 0u);
         }
-        __syncwarp();
+    } else if constexpr (AUX_BF16) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int grow = m_base + 4 * i + rrow;
+            auxh[i] = (col_ok && grow < p.M) ? *reinterpret_cast<const uint2*>(p.aux + static_cast<int64_t>(grow) * p.ldaux + col)
+                                             : make_uint2(0u, 0u);
+        }
+    }
+    float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+    if (p.bias != nullptr && col_ok) {
+        const uint2 bb = __ldg(reinterpret_cast<const uint2*>(p.bias + col));
+        const float2 f0 = unpack_bf16(bb.x), f1 = unpack_bf16(bb.y);
+        b0 = f0.x; b1 = f0.y; b2 = f1.x; b3 = f1.y;
+    }
+    // ---- transpose: row layout -> staging
+    tmem_ld_wait();
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) = make_uint4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
+    __syncwarp();
+    // ---- coalesced layout: maths + stores
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + rrow;
+        const int grow = m_base + row;
+        const uint4 v = *reinterpret_cast<const uint4*>(stg + stage_off(row, rch));
+        float x0 = fmaf(__uint_as_float(v.x), scale, b0), x1 = fmaf(__uint_as_float(v.y), scale, b1);
+        float x2 = fmaf(__uint_as_float(v.z), scale, b2), x3 = fmaf(__uint_as_float(v.w), scale, b3);
+        const bool ok = col_ok && grow < p.M;
         if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
-            if (p.preact != nullptr) {  // second output: the pre-activation (saved for the backward)
-#pragma unroll
-                for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) = pre[c];
-                __syncwarp();
-                uint8_t* Pb = reinterpret_cast<uint8_t*>(p.preact);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int row = 4 * i + rrow;
-                    const int grow = m_base + row, col = col0 + rch * EPC;
-                    const uint4 v = *reinterpret_cast<const uint4*>(stg + stage_off(row, rch));
-                    if (grow < p.M && col < p.N)
-                        *reinterpret_cast<uint4*>(Pb + (static_cast<int64_t>(grow) * p.ldc + col) * ESZ) = v;
-                }
-                __syncwarp();
+            if (p.preact != nullptr && ok)
+                *reinterpret_cast<uint2*>(p.preact + static_cast<int64_t>(grow) * p.ldc + col) =
+                    make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+            x0 = qgelu_fast(x0); x1 = qgelu_fast(x1); x2 = qgelu_fast(x2); x3 = qgelu_fast(x3);
+        } else if constexpr (AUX_F32) {
+            x0 += __uint_as_float(auxf[i].x); x1 += __uint_as_float(auxf[i].y);
+            x2 += __uint_as_float(auxf[i].z); x3 += __uint_as_float(auxf[i].w);
+        } else if constexpr (AUX_BF16) {
+            const float2 f0 = unpack_bf16(auxh[i].x), f1 = unpack_bf16(auxh[i].y);
+            if constexpr (EPI == B200CLIP_EPI_RESIDUAL) {
+                x0 += f0.x; x1 += f0.y; x2 += f1.x; x3 += f1.y;
+            } else {
+                x0 = qgelu_bwd_fast(x0, f0.x); x1 = qgelu_bwd_fast(x1, f0.y);
+                x2 = qgelu_bwd_fast(x2, f1.x); x3 = qgelu_bwd_fast(x3, f1.y);
+            }
+        }
+        if (ok) {
+            if constexpr (OUT_F32) {
+                float* dst = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(grow) * p.ldc + col;
+                if constexpr (ATOMIC)
+                    red_add_v4(dst, x0, x1, x2, x3);
+                else
+                    *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
+            } else {
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(grow) * p.ldc + col) =
+                    make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
             }
         }
     }
+    __syncwarp();  // the staging tile is rewritten by the next block
+}
+
+// drains `ncols` accumulator columns (a multiple of 32) starting at TMEM address taddr
+template <int EPI, bool OUT_F32, bool ATOMIC>
+__device__ __forceinline__ void epilogue_run(const GemmParams& p, uint32_t taddr, int m_base, int n_base, int ncols,
+                                             float scale, uint8_t* stg, int lane) {
+    int nblk = ncols >> 5;
+    const int valid = (p.N - n_base + 31) >> 5;  // blocks that contain at least one real column (warp-uniform)
+    if (valid < nblk) nblk = valid;
+    if (nblk <= 0) return;
+#pragma unroll 1
+    for (int j = 0; j < nblk; ++j)
+        epilogue_block<EPI, OUT_F32, ATOMIC>(p, taddr + j * 32, m_base, n_base + j * 32, scale, stg, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -407,36 +323,27 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                    static_cast<uint32_t>(as * BN + half * (BN / 2));
             const int m_base = m0 + quad * 32;
-            if (p.atomic_out) {
-                // split-K / accumulate: fp32 atomics straight from the row layout
-                const int row = m_base + lane;
-#pragma unroll 1
-                for (int c = 0; c < BN / 64; ++c) {
-                    const int col0 = n0 + c * 32;
-                    if (col0 >= p.N) break;  // warp-uniform
-                    uint32_t acc[32];
-                    tmem_ld_32x32(taddr + c * 32, acc);
-                    tmem_ld_wait();
-                    epilogue_chunk<B200CLIP_EPI_NONE, true, true>(p, acc, row, col0, scale);
-                }
-            } else if (p.out_f32) {
-                if (p.epilogue == B200CLIP_EPI_RESIDUAL)
-                    epilogue_staged<B200CLIP_EPI_RESIDUAL, true>(p, taddr, m_base, n0, BN / 2, scale, stg, lane);
+            constexpr int HW = BN / 2;
+            if (p.out_f32) {
+                if (p.atomic_out)
+                    epilogue_run<B200CLIP_EPI_NONE, true, true>(p, taddr, m_base, n0, HW, scale, stg, lane);
+                else if (p.epilogue == B200CLIP_EPI_RESIDUAL)
+                    epilogue_run<B200CLIP_EPI_RESIDUAL, true, false>(p, taddr, m_base, n0, HW, scale, stg, lane);
                 else
-                    epilogue_staged<B200CLIP_EPI_NONE, true>(p, taddr, m_base, n0, BN / 2, scale, stg, lane);
+                    epilogue_run<B200CLIP_EPI_NONE, true, false>(p, taddr, m_base, n0, HW, scale, stg, lane);
             } else {
                 switch (p.epilogue) {
                     case B200CLIP_EPI_QUICKGELU:
-                        epilogue_staged<B200CLIP_EPI_QUICKGELU, false>(p, taddr, m_base, n0, BN / 2, scale, stg, lane);
+                        epilogue_run<B200CLIP_EPI_QUICKGELU, false, false>(p, taddr, m_base, n0, HW, scale, stg, lane);
                         break;
                     case B200CLIP_EPI_RESIDUAL:
-                        epilogue_staged<B200CLIP_EPI_RESIDUAL, false>(p, taddr, m_base, n0, BN / 2, scale, stg, lane);
+                        epilogue_run<B200CLIP_EPI_RESIDUAL, false, false>(p, taddr, m_base, n0, HW, scale, stg, lane);
                         break;
                     case B200CLIP_EPI_QUICKGELU_BWD:
-                        epilogue_staged<B200CLIP_EPI_QUICKGELU_BWD, false>(p, taddr, m_base, n0, BN / 2, scale, stg, lane);
+                        epilogue_run<B200CLIP_EPI_QUICKGELU_BWD, false, false>(p, taddr, m_base, n0, HW, scale, stg, lane);
                         break;
                     default:
-                        epilogue_staged<B200CLIP_EPI_NONE, false>(p, taddr, m_base, n0, BN / 2, scale, stg, lane);
+                        epilogue_run<B200CLIP_EPI_NONE, false, false>(p, taddr, m_base, n0, HW, scale, stg, lane);
                         break;
                 }
             }
