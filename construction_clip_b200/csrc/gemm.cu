@@ -84,43 +84,59 @@ __device__ __forceinline__ float qgelu_bwd_fast(float acc, float x) {
     return fmaf(h, c, h);
 }
 
+// per-lane operands of one 32x32 block that do not depend on the accumulator: aux (coalesced layout:
+// 8 rows x 4 columns) and bias (4 columns).  Fetched one block ahead so that global-memory latency
+// is off the critical path (the first block of a tile is fetched before waiting for the MMA).
+template <int EPI, bool OUT_F32>
+struct EpiOperands {
+    static constexpr bool AUX_F32 = (EPI == B200CLIP_EPI_RESIDUAL) && OUT_F32;
+    static constexpr bool AUX_BF16 = (EPI == B200CLIP_EPI_QUICKGELU_BWD) || (EPI == B200CLIP_EPI_RESIDUAL && !OUT_F32);
+    uint4 auxf[AUX_F32 ? 8 : 1];
+    uint2 auxh[AUX_BF16 ? 8 : 1];
+    float b0, b1, b2, b3;
+
+    __device__ __forceinline__ void load(const GemmParams& p, int m_base, int col0, int lane) {
+        const int rrow = lane >> 3, col = col0 + (lane & 7) * 4;
+        const bool col_ok = col < p.N;  // N % 8 == 0 and col % 4 == 0: the 4 columns are all in or all out
+        if constexpr (AUX_F32) {
+            const float* ap = reinterpret_cast<const float*>(p.aux);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int grow = m_base + 4 * i + rrow;
+                auxf[i] = (col_ok && grow < p.M)
+                              ? *reinterpret_cast<const uint4*>(ap + static_cast<int64_t>(grow) * p.ldaux + col)
+                              : make_uint4(0u, 0u, 0u, 0u);
+            }
+        }
+        if constexpr (AUX_BF16) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int grow = m_base + 4 * i + rrow;
+                auxh[i] = (col_ok && grow < p.M)
+                              ? *reinterpret_cast<const uint2*>(p.aux + static_cast<int64_t>(grow) * p.ldaux + col)
+                              : make_uint2(0u, 0u);
+            }
+        }
+        b0 = b1 = b2 = b3 = 0.f;
+        if (p.bias != nullptr && col_ok) {
+            const uint2 bb = __ldg(reinterpret_cast<const uint2*>(p.bias + col));
+            const float2 f0 = unpack_bf16(bb.x), f1 = unpack_bf16(bb.y);
+            b0 = f0.x; b1 = f0.y; b2 = f1.x; b3 = f1.y;
+        }
+    }
+};
+
 template <int EPI, bool OUT_F32, bool ATOMIC>
-__device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t taddr, int m_base, int col0, float scale,
-                                               uint8_t* stg, int lane) {
-    uint32_t acc[32];
-    tmem_ld_32x32(taddr, acc);  // asynchronous until tcgen05.wait::ld below
-    constexpr bool AUX_F32 = (EPI == B200CLIP_EPI_RESIDUAL) && OUT_F32;
-    constexpr bool AUX_BF16 = (EPI == B200CLIP_EPI_QUICKGELU_BWD) || (EPI == B200CLIP_EPI_RESIDUAL && !OUT_F32);
+__device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOperands<EPI, OUT_F32>& op, uint32_t taddr,
+                                               int m_base, int col0, float scale, uint8_t* stg, int lane) {
+    using Op = EpiOperands<EPI, OUT_F32>;
     const int rrow = lane >> 3, rch = lane & 7;
     const int col = col0 + rch * 4;
-    const bool col_ok = col < p.N;  // N % 8 == 0 and col % 4 == 0: the 4 columns are all in or all out
-    // ---- loads that do not depend on the transpose: aux (coalesced) and bias
-    [[maybe_unused]] uint4 auxf[8];
-    [[maybe_unused]] uint2 auxh[8];
-    if constexpr (AUX_F32) {
-        const float* ap = reinterpret_cast<const float*>(p.aux);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int grow = m_base + 4 * i + rrow;
-            auxf[i] = (col_ok && grow < p.M) ? *reinterpret_cast<const uint4*>(ap + static_cast<int64_t>(grow) * p.ldaux + col)
-                                             : make_uint4(0u, 0u, 0u, 0u);
-        }
-    } else if constexpr (AUX_BF16) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int grow = m_base + 4 * i + rrow;
-            auxh[i] = (col_ok && grow < p.M) ? *reinterpret_cast<const uint2*>(p.aux + static_cast<int64_t>(grow) * p.ldaux + col)
-                                             : make_uint2(0u, 0u);
-        }
-    }
-    float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-    if (p.bias != nullptr && col_ok) {
-        const uint2 bb = __ldg(reinterpret_cast<const uint2*>(p.bias + col));
-        const float2 f0 = unpack_bf16(bb.x), f1 = unpack_bf16(bb.y);
-        b0 = f0.x; b1 = f0.y; b2 = f1.x; b3 = f1.y;
-    }
-    // ---- transpose: row layout -> staging
+    const bool col_ok = col < p.N;
+    uint32_t acc[32];
+    tmem_ld_32x32(taddr, acc);
     tmem_ld_wait();
+    // ---- transpose: row layout -> staging
 #pragma unroll
     for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) = make_uint4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
@@ -131,19 +147,19 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t tad
         const int row = 4 * i + rrow;
         const int grow = m_base + row;
         const uint4 v = *reinterpret_cast<const uint4*>(stg + stage_off(row, rch));
-        float x0 = fmaf(__uint_as_float(v.x), scale, b0), x1 = fmaf(__uint_as_float(v.y), scale, b1);
-        float x2 = fmaf(__uint_as_float(v.z), scale, b2), x3 = fmaf(__uint_as_float(v.w), scale, b3);
+        float x0 = fmaf(__uint_as_float(v.x), scale, op.b0), x1 = fmaf(__uint_as_float(v.y), scale, op.b1);
+        float x2 = fmaf(__uint_as_float(v.z), scale, op.b2), x3 = fmaf(__uint_as_float(v.w), scale, op.b3);
         const bool ok = col_ok && grow < p.M;
         if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
             if (p.preact != nullptr && ok)
                 *reinterpret_cast<uint2*>(p.preact + static_cast<int64_t>(grow) * p.ldc + col) =
                     make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
             x0 = qgelu_fast(x0); x1 = qgelu_fast(x1); x2 = qgelu_fast(x2); x3 = qgelu_fast(x3);
-        } else if constexpr (AUX_F32) {
-            x0 += __uint_as_float(auxf[i].x); x1 += __uint_as_float(auxf[i].y);
-            x2 += __uint_as_float(auxf[i].z); x3 += __uint_as_float(auxf[i].w);
-        } else if constexpr (AUX_BF16) {
-            const float2 f0 = unpack_bf16(auxh[i].x), f1 = unpack_bf16(auxh[i].y);
+        } else if constexpr (Op::AUX_F32) {
+            x0 += __uint_as_float(op.auxf[i].x); x1 += __uint_as_float(op.auxf[i].y);
+            x2 += __uint_as_float(op.auxf[i].z); x3 += __uint_as_float(op.auxf[i].w);
+        } else if constexpr (Op::AUX_BF16) {
+            const float2 f0 = unpack_bf16(op.auxh[i].x), f1 = unpack_bf16(op.auxh[i].y);
             if constexpr (EPI == B200CLIP_EPI_RESIDUAL) {
                 x0 += f0.x; x1 += f0.y; x2 += f1.x; x3 += f1.y;
             } else {
@@ -167,17 +183,43 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, uint32_t tad
     __syncwarp();  // the staging tile is rewritten by the next block
 }
 
-// drains `ncols` accumulator columns (a multiple of 32) starting at TMEM address taddr
-template <int EPI, bool OUT_F32, bool ATOMIC>
-__device__ __forceinline__ void epilogue_run(const GemmParams& p, uint32_t taddr, int m_base, int n_base, int ncols,
-                                             float scale, uint8_t* stg, int lane) {
-    int nblk = ncols >> 5;
-    const int valid = (p.N - n_base + 31) >> 5;  // blocks that contain at least one real column (warp-uniform)
-    if (valid < nblk) nblk = valid;
-    if (nblk <= 0) return;
+// The whole persistent loop of one epilogue warp, specialised on the epilogue flavour.
+template <int BN, int EPI, bool OUT_F32, bool ATOMIC>
+__device__ __noinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
+                                           uint64_t* tmem_empty_bar, uint8_t* stg, int warp, int lane, int num_work) {
+    const int quad = warp & 3;         // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
+    const float scale = (p.scale != nullptr) ? __ldg(p.scale) : 1.0f;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int tile = w / p.split_k;
+        const int m_base = (tile / p.num_n_tiles) * BM + quad * 32;
+        const int n_base = (tile % p.num_n_tiles) * BN + half * (BN / 2);
+        int nblk = (BN / 2) >> 5;
+        const int valid = (p.N - n_base + 31) >> 5;  // blocks with at least one real column (warp-uniform)
+        if (valid < nblk) nblk = valid;
+        EpiOperands<EPI, OUT_F32> cur, nxt;
+        if (nblk > 0) cur.load(p, m_base, n_base, lane);  // before waiting for the accumulator
+        mbar_wait(&tmem_full_bar[as], aphase);
+        __syncwarp();
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
+                               static_cast<uint32_t>(as * BN + half * (BN / 2));
 #pragma unroll 1
-    for (int j = 0; j < nblk; ++j)
-        epilogue_block<EPI, OUT_F32, ATOMIC>(p, taddr + j * 32, m_base, n_base + j * 32, scale, stg, lane);
+        for (int j = 0; j < nblk; ++j) {
+            if (j + 1 < nblk) nxt.load(p, m_base, n_base + (j + 1) * 32, lane);
+            epilogue_block<EPI, OUT_F32, ATOMIC>(p, cur, taddr + j * 32, m_base, n_base + j * 32, scale, stg, lane);
+            cur = nxt;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        if (++as == 2) {
+            as = 0;
+            aphase ^= 1u;
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -307,54 +349,25 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
     } else {
         // ===================================== epilogue warps ===================================
-        const int quad = warp & 3;           // TMEM lane quadrant this warp may access
-        const int half = (warp - 2) >> 2;    // which half of the tile's columns this warp drains
         uint8_t* stg = smem + kStages * Cfg::kStageBytes + (warp - 2) * kEpiStageBytes;
-        int as = 0;
-        uint32_t aphase = 0;
-        const float scale = (p.scale != nullptr) ? __ldg(p.scale) : 1.0f;
-        for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-            const int tile = w / p.split_k;
-            const int m0 = (tile / p.num_n_tiles) * BM;
-            const int n0 = (tile % p.num_n_tiles) * BN + half * (BN / 2);
-            mbar_wait(&tmem_full_bar[as], aphase);
-            __syncwarp();
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                                   static_cast<uint32_t>(as * BN + half * (BN / 2));
-            const int m_base = m0 + quad * 32;
-            constexpr int HW = BN / 2;
-            if (p.out_f32) {
-                if (p.atomic_out)
-                    epilogue_run<B200CLIP_EPI_NONE, true, true>(p, taddr, m_base, n0, HW, scale, stg, lane);
-                else if (p.epilogue == B200CLIP_EPI_RESIDUAL)
-                    epilogue_run<B200CLIP_EPI_RESIDUAL, true, false>(p, taddr, m_base, n0, HW, scale, stg, lane);
-                else
-                    epilogue_run<B200CLIP_EPI_NONE, true, false>(p, taddr, m_base, n0, HW, scale, stg, lane);
-            } else {
-                switch (p.epilogue) {
-                    case B200CLIP_EPI_QUICKGELU:
-                        epilogue_run<B200CLIP_EPI_QUICKGELU, false, false>(p, taddr, m_base, n0, HW, scale, stg, lane);
-                        break;
-                    case B200CLIP_EPI_RESIDUAL:
-                        epilogue_run<B200CLIP_EPI_RESIDUAL, false, false>(p, taddr, m_base, n0, HW, scale, stg, lane);
-                        break;
-                    case B200CLIP_EPI_QUICKGELU_BWD:
-                        epilogue_run<B200CLIP_EPI_QUICKGELU_BWD, false, false>(p, taddr, m_base, n0, HW, scale, stg, lane);
-                        break;
-                    default:
-                        epilogue_run<B200CLIP_EPI_NONE, false, false>(p, taddr, m_base, n0, HW, scale, stg, lane);
-                        break;
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
-            if (++as == 2) {
-                as = 0;
-                aphase ^= 1u;
+#define EPI_LOOP(E, F32, AT) \
+    epilogue_loop<BN, E, F32, AT>(p, tmem_base, tmem_full_bar, tmem_empty_bar, stg, warp, lane, num_work)
+        if (p.out_f32) {
+            if (p.atomic_out)
+                EPI_LOOP(B200CLIP_EPI_NONE, true, true);
+            else if (p.epilogue == B200CLIP_EPI_RESIDUAL)
+                EPI_LOOP(B200CLIP_EPI_RESIDUAL, true, false);
+            else
+                EPI_LOOP(B200CLIP_EPI_NONE, true, false);
+        } else {
+            switch (p.epilogue) {
+                case B200CLIP_EPI_QUICKGELU: EPI_LOOP(B200CLIP_EPI_QUICKGELU, false, false); break;
+                case B200CLIP_EPI_RESIDUAL: EPI_LOOP(B200CLIP_EPI_RESIDUAL, false, false); break;
+                case B200CLIP_EPI_QUICKGELU_BWD: EPI_LOOP(B200CLIP_EPI_QUICKGELU_BWD, false, false); break;
+                default: EPI_LOOP(B200CLIP_EPI_NONE, false, false); break;
             }
         }
+#undef EPI_LOOP
     }
 
     tc_fence_before();
