@@ -185,7 +185,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
 
 // The whole persistent loop of one epilogue warp, specialised on the epilogue flavour.
 template <int BN, int EPI, bool OUT_F32, bool ATOMIC>
-__device__ __noinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
+__device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
                                            uint64_t* tmem_empty_bar, uint8_t* stg, int warp, int lane, int num_work) {
     const int quad = warp & 3;         // TMEM lane quadrant this warp may access
     const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
