@@ -95,30 +95,31 @@ struct EpiOperands {
     uint2 auxh[AUX_BF16 ? 8 : 1];
     float b0, b1, b2, b3;
 
+    // Loads are UNCONDITIONAL from clamped (always valid) addresses so that all eight are in flight
+    // at once -- a `cond ? load : 0` select puts a dependent MOV behind every load and serialises
+    // them.  Values fetched for out-of-range rows / columns are never stored.
     __device__ __forceinline__ void load(const GemmParams& p, int m_base, int col0, int lane) {
-        const int rrow = lane >> 3, col = col0 + (lane & 7) * 4;
-        const bool col_ok = col < p.N;  // N % 8 == 0 and col % 4 == 0: the 4 columns are all in or all out
+        const int rrow = lane >> 3;
+        int col = col0 + (lane & 7) * 4;
+        col = col < p.N ? col : 0;  // N % 8 == 0 and col % 4 == 0: the 4 columns are all in or all out
         if constexpr (AUX_F32) {
-            const float* ap = reinterpret_cast<const float*>(p.aux);
+            const float* ap = reinterpret_cast<const float*>(p.aux) + col;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int grow = m_base + 4 * i + rrow;
-                auxf[i] = (col_ok && grow < p.M)
-                              ? *reinterpret_cast<const uint4*>(ap + static_cast<int64_t>(grow) * p.ldaux + col)
-                              : make_uint4(0u, 0u, 0u, 0u);
+                const int grow = min(m_base + 4 * i + rrow, p.M - 1);
+                auxf[i] = *reinterpret_cast<const uint4*>(ap + static_cast<int64_t>(grow) * p.ldaux);
             }
         }
         if constexpr (AUX_BF16) {
+            const __nv_bfloat16* ap = p.aux + col;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                const int grow = m_base + 4 * i + rrow;
-                auxh[i] = (col_ok && grow < p.M)
-                              ? *reinterpret_cast<const uint2*>(p.aux + static_cast<int64_t>(grow) * p.ldaux + col)
-                              : make_uint2(0u, 0u);
+                const int grow = min(m_base + 4 * i + rrow, p.M - 1);
+                auxh[i] = *reinterpret_cast<const uint2*>(ap + static_cast<int64_t>(grow) * p.ldaux);
             }
         }
         b0 = b1 = b2 = b3 = 0.f;
-        if (p.bias != nullptr && col_ok) {
+        if (p.bias != nullptr) {
             const uint2 bb = __ldg(reinterpret_cast<const uint2*>(p.bias + col));
             const float2 f0 = unpack_bf16(bb.x), f1 = unpack_bf16(bb.y);
             b0 = f0.x; b1 = f0.y; b2 = f1.x; b3 = f1.y;
@@ -199,18 +200,22 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
         int nblk = (BN / 2) >> 5;
         const int valid = (p.N - n_base + 31) >> 5;  // blocks with at least one real column (warp-uniform)
         if (valid < nblk) nblk = valid;
-        EpiOperands<EPI, OUT_F32> cur, nxt;
-        if (nblk > 0) cur.load(p, m_base, n_base, lane);  // before waiting for the accumulator
+        EpiOperands<EPI, OUT_F32> opA, opB;  // ping-pong: the next block's operands load while this one runs
+        if (nblk > 0) opA.load(p, m_base, n_base, lane);  // before waiting for the accumulator
         mbar_wait(&tmem_full_bar[as], aphase);
         __syncwarp();
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                static_cast<uint32_t>(as * BN + half * (BN / 2));
 #pragma unroll 1
-        for (int j = 0; j < nblk; ++j) {
-            if (j + 1 < nblk) nxt.load(p, m_base, n_base + (j + 1) * 32, lane);
-            epilogue_block<EPI, OUT_F32, ATOMIC>(p, cur, taddr + j * 32, m_base, n_base + j * 32, scale, stg, lane);
-            cur = nxt;
+        for (int j = 0; j < nblk; j += 2) {
+            if (j + 1 < nblk) opB.load(p, m_base, n_base + (j + 1) * 32, lane);
+            epilogue_block<EPI, OUT_F32, ATOMIC>(p, opA, taddr + j * 32, m_base, n_base + j * 32, scale, stg, lane);
+            if (j + 1 < nblk) {
+                if (j + 2 < nblk) opA.load(p, m_base, n_base + (j + 2) * 32, lane);
+                epilogue_block<EPI, OUT_F32, ATOMIC>(p, opB, taddr + (j + 1) * 32, m_base, n_base + (j + 1) * 32, scale,
+                                                     stg, lane);
+            }
         }
         tc_fence_before();
         __syncwarp();

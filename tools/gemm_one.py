@@ -20,6 +20,9 @@ elif case.endswith("out_fwd"):
 elif case.endswith("fc_dgrad"):
     w = torch.randn(4 * d, d, device=dev).to(bf16)
     fn = lambda: O.gemm(x4, w, b_major=L.MAJOR_MN)
+elif case.endswith("proj_dgrad"):
+    w = torch.randn(d, 4 * d, device=dev).to(bf16)
+    fn = lambda: O.gemm(x, w, b_major=L.MAJOR_MN, epilogue=L.EPI_QUICKGELU_BWD, aux=x4)
 elif case.endswith("qkv_fwd"):
     w = torch.randn(3 * d, d, device=dev).to(bf16); b = torch.randn(3 * d, device=dev).to(bf16)
     fn = lambda: O.gemm(x, w, bias=b)
