@@ -1,0 +1,97 @@
+"""Multi-GPU parity check (run under torchrun): the R-rank sharded step must equal the
+single-device step on the concatenated global batch (loss within 1e-3 relative, gradients equal
+up to reduction order)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    from helpers import SEED, cosine, device_model, oracle_model
+    from oracle import clip_oracle as O
+    from construction_clip_b200.train import ClipTrainer, clip_contrastive_loss
+
+    name = os.environ.get("DIST_MODEL", "ViT-B/32")
+    Bg = int(os.environ.get("DIST_BATCH", "16"))
+    cfg = O.CONFIGS[name]
+    orc = oracle_model(name)
+    img = O.synth_images(Bg, cfg.image_resolution, seed=SEED)
+    tok = O.synth_tokens(Bg, seed=SEED, min_len=3, max_len=20)
+    bl = Bg // world
+    sl = slice(rank * bl, (rank + 1) * bl)
+
+    # sharded trainer step (flat fp32 grads, all-reduced)
+    m = device_model(name, orc, device=dev).train()
+    tr = ClipTrainer(m, lr=1e-4, warmup_steps=0)
+    loss = tr.forward_backward(img[sl].to(dev), tok[sl].to(dev))
+    torch.cuda.synchronize()
+    flat_sharded = {k: v.clone() for k, v in tr.grads.items()}
+    d_ls_sharded = tr.d_ls.clone()
+
+    # single-device reference on the full batch (every rank computes it redundantly)
+    m1 = device_model(name, orc, device=dev).train()
+    tr1 = ClipTrainer(m1, lr=1e-4, warmup_steps=0, group=None)
+    tr1.world, tr1.rank = 1, 0
+    # a 1-rank "group": run the loss without collectives
+    import construction_clip_b200.train as T
+    real_world = T._world
+    T._world = lambda g: (1, 0)
+    try:
+        loss1 = tr1.forward_backward(img.to(dev), tok.to(dev))
+    finally:
+        T._world = real_world
+    torch.cuda.synchronize()
+    ok = True
+    rel = abs(loss.item() - loss1.item()) / abs(loss1.item())
+    if rel > 1e-3:
+        ok = False
+    worst = 1.0
+    for k in flat_sharded:
+        c = cosine(flat_sharded[k], tr1.grads[k])
+        worst = min(worst, c)
+        n0, n1 = flat_sharded[k].norm().item(), tr1.grads[k].norm().item()
+        if c < 0.999 or abs(n0 - n1) > 0.02 * n1:
+            ok = False
+    dls = abs(d_ls_sharded.item() - tr1.d_ls.item()) / max(1e-9, abs(tr1.d_ls.item()))
+    if dls > 2e-2:
+        ok = False
+    # autograd API: per-rank .grad holds the local share; their sum equals the full gradient
+    m2 = device_model(name, orc, device=dev).train()
+    l2 = clip_contrastive_loss(m2, img[sl].to(dev), tok[sl].to(dev))
+    l2.backward()
+    g = m2.visual.proj.grad.float().clone()
+    dist.all_reduce(g)
+    ref = tr1.G["visual"]["proj"]
+    c2 = cosine(g, ref)
+    if c2 < 0.999 or abs(l2.item() - loss1.item()) > 1e-3 * abs(loss1.item()):
+        ok = False
+    # optimizer step keeps replicas identical
+    tr.optimizer_step()
+    w = tr.stores["visual"].w.float()
+    w0 = w.clone()
+    dist.broadcast(w0, 0)
+    same = torch.equal(w, w0)
+    if not same:
+        ok = False
+    flag = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        print(f"DIST_CHECK world={world} Bg={Bg} loss_sharded={loss.item():.6f} loss_single={loss1.item():.6f} rel={rel:.2e} "
+              f"worst_grad_cos={worst:.6f} dls_rel={dls:.2e} autograd_cos={c2:.6f} replicas_identical={same} "
+              f"RESULT={'PASS' if flag.item() == 1.0 else 'FAIL'}", flush=True)
+    dist.destroy_process_group()
+    sys.exit(0 if flag.item() == 1.0 else 1)
+
+
+if __name__ == "__main__":
+    main()
