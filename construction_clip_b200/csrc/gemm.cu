@@ -41,6 +41,7 @@ struct GemmParams {
     const __nv_bfloat16* aux;
     __nv_bfloat16* preact;
     const float* scale;
+    float* colsum;  // optional fp32 [N]: += column sums of C (bias gradient of the layer that produced A's grad)
     int64_t ldc, ldaux;
     int M, N, K;
     int num_m_tiles, num_n_tiles;
@@ -143,6 +144,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
         *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) = make_uint4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
     __syncwarp();
     // ---- coalesced layout: maths + stores
+    float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int row = 4 * i + rrow;
@@ -169,6 +171,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
             }
         }
         if (ok) {
+            cs0 += x0; cs1 += x1; cs2 += x2; cs3 += x3;
             if constexpr (OUT_F32) {
                 float* dst = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(grow) * p.ldc + col;
                 if constexpr (ATOMIC)
@@ -180,6 +183,14 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
                     make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
             }
         }
+    }
+    if (p.colsum != nullptr) {  // warp-uniform
+        // lanes l, l^8, l^16, l^24 hold the same 4 columns for different rows
+        cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+        cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
+        cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+        cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
+        if (lane < 8 && col_ok) red_add_v4(p.colsum + col, cs0, cs1, cs2, cs3);
     }
     __syncwarp();  // the staging tile is rewritten by the next block
 }
@@ -453,8 +464,9 @@ using namespace b200;
 
 extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda, int a_major, const void* B,
                                   int64_t ldb, int b_major, void* C, int64_t ldc, int out_dtype, const void* bias,
-                                  const void* aux, int64_t ldaux, void* preact, const float* scale, int64_t M,
-                                  int64_t N, int64_t K, int epilogue, int split_k, int accumulate, void* stream) {
+                                  const void* aux, int64_t ldaux, void* preact, const float* scale, float* colsum,
+                                  int64_t M, int64_t N, int64_t K, int epilogue, int split_k, int accumulate,
+                                  void* stream) {
     B200_CHECK_CTX(ctx);
     B200_CHECK_ARG(A && B && C, "gemm: null operand");
     B200_CHECK_ARG(M > 0 && N > 0 && K > 0, "gemm: empty problem %lld x %lld x %lld", (long long)M, (long long)N,
@@ -485,6 +497,8 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
     }
     B200_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias not 16B aligned");
     B200_CHECK_ARG(preact == nullptr || (reinterpret_cast<uintptr_t>(preact) & 15) == 0, "gemm: preact misaligned");
+    B200_CHECK_ARG(colsum == nullptr || ((reinterpret_cast<uintptr_t>(colsum) & 15) == 0 && split_k == 1 && !accumulate),
+                   "gemm: colsum needs a 16-byte aligned pointer and a non-split, non-accumulating GEMM");
 
     GemmParams p{};
     p.C = C;
@@ -492,6 +506,7 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
     p.aux = static_cast<const __nv_bfloat16*>(aux);
     p.preact = static_cast<__nv_bfloat16*>(preact);
     p.scale = scale;
+    p.colsum = colsum;
     p.ldc = ldc;
     p.ldaux = ldaux;
     p.M = static_cast<int>(M);

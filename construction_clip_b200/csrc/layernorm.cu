@@ -131,96 +131,110 @@ layernorm_fwd_kernel(const TX* __restrict__ x, int64_t ldx, const int32_t* __res
 }
 
 // dx = dres + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma,  xhat = (x-mean)*rstd
-template <int NV, typename TX>
-__global__ void __launch_bounds__(kLnThreads)
+// Two passes over the row: pass 1 accumulates the two row reductions and the per-column partial sums
+// of dgamma / dbeta; pass 2 re-reads x, dy (L1 hits: a row is a few KB) and writes dx.  Only the
+// column accumulators live across rows, which keeps the kernel at <= 128 registers and 16 warps / SM.
+template <int NV, typename TX, bool COLSUM>
+__global__ void __launch_bounds__(kLnThreads, (NV <= 3) ? 2 : 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const TX* __restrict__ x,
                      int64_t ldx, const int32_t* __restrict__ row_index, const __nv_bfloat16* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const __nv_bfloat16* __restrict__ dres, int64_t lddres, __nv_bfloat16* __restrict__ dx,
-                     int64_t lddx, float* __restrict__ dgamma, float* __restrict__ dbeta, int rows, int d) {
-    extern __shared__ float s_acc[];  // [2][d]
+                     int64_t lddx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                     float* __restrict__ dx_colsum, int rows, int d) {
+    extern __shared__ float s_acc[];  // [3][d]
     const int lane = threadIdx.x & 31;
     const int warps_per_block = kLnThreads / 32;
     const int nvec = d >> 3;
-    for (int i = threadIdx.x; i < 2 * d; i += kLnThreads) s_acc[i] = 0.f;
+    for (int i = threadIdx.x; i < 3 * d; i += kLnThreads) s_acc[i] = 0.f;
     __syncthreads();
 
     float ag[NV][8], ab[NV][8];
+    float ac[COLSUM ? NV : 1][8];
 #pragma unroll
     for (int i = 0; i < NV; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) ag[i][j] = ab[i][j] = 0.f;
+        for (int j = 0; j < 8; ++j) {
+            ag[i][j] = ab[i][j] = 0.f;
+            if constexpr (COLSUM) ac[i][j] = 0.f;
+        }
     for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
         const int64_t src = row_index ? row_index[r] : r;
         const float mu = mean[r], rs = rstd[r];
-        float xh[NV][8], g[NV][8];
+        const TX* xr = x + src * ldx;
+        const __nv_bfloat16* dyr = dy + static_cast<int64_t>(r) * lddy;
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int vec = lane + 32 * i;
             if (vec < nvec) {
                 float xf[8], df[8], gf[8];
-                load8(x + src * ldx + vec * 8, xf);
-                load8(dy + static_cast<int64_t>(r) * lddy + vec * 8, df);
+                load8(xr + vec * 8, xf);
+                load8(dyr + vec * 8, df);
                 load8(gamma + vec * 8, gf);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    xh[i][j] = (xf[j] - mu) * rs;
+                    const float xh = (xf[j] - mu) * rs;
+                    const float g = df[j] * gf[j];
                     ab[i][j] += df[j];
-                    ag[i][j] += df[j] * xh[i][j];
-                    g[i][j] = df[j] * gf[j];
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    s1 += g[i][j];
-                    s2 += g[i][j] * xh[i][j];
+                    ag[i][j] = fmaf(df[j], xh, ag[i][j]);
+                    s1 += g;
+                    s2 = fmaf(g, xh, s2);
                 }
             }
         }
         s1 = warp_sum(s1) / d;
         s2 = warp_sum(s2) / d;
+        __nv_bfloat16* dxr = dx + src * lddx;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int vec = lane + 32 * i;
             if (vec < nvec) {
-                float o[8];
+                float xf[8], df[8], gf[8], o[8];
+                load8(xr + vec * 8, xf);
+                load8(dyr + vec * 8, df);
+                load8(gamma + vec * 8, gf);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) o[j] = rs * (g[i][j] - s1 - xh[i][j] * s2);
-                if (dres != nullptr) {
-                    const uint4 ur = *reinterpret_cast<const uint4*>(dres + static_cast<int64_t>(r) * lddres + vec * 8);
-                    const uint32_t rw[4] = {ur.x, ur.y, ur.z, ur.w};
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const float2 f = unpack_bf16(rw[j]);
-                        o[2 * j] += f.x;
-                        o[2 * j + 1] += f.y;
-                    }
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (xf[j] - mu) * rs;
+                    o[j] = rs * (df[j] * gf[j] - s1 - xh * s2);
                 }
-                uint4 ov;
-                ov.x = pack_bf16(o[0], o[1]);
-                ov.y = pack_bf16(o[2], o[3]);
-                ov.z = pack_bf16(o[4], o[5]);
-                ov.w = pack_bf16(o[6], o[7]);
-                *reinterpret_cast<uint4*>(dx + src * lddx + vec * 8) = ov;
+                if (dres != nullptr) {
+                    float rf[8];
+                    load8(dres + static_cast<int64_t>(r) * lddres + vec * 8, rf);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o[j] += rf[j];
+                }
+                store8(dxr + vec * 8, o);
+                if constexpr (COLSUM) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) ac[i][j] += o[j];
+                }
             }
         }
     }
-    if (dgamma != nullptr) {
+    if (dgamma != nullptr || COLSUM) {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int vec = lane + 32 * i;
             if (vec < nvec) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    atomicAdd(&s_acc[vec * 8 + j], ag[i][j]);
-                    atomicAdd(&s_acc[d + vec * 8 + j], ab[i][j]);
+                    if (dgamma != nullptr) {
+                        atomicAdd(&s_acc[vec * 8 + j], ag[i][j]);
+                        atomicAdd(&s_acc[d + vec * 8 + j], ab[i][j]);
+                    }
+                    if constexpr (COLSUM) atomicAdd(&s_acc[2 * d + vec * 8 + j], ac[i][j]);
                 }
             }
         }
         __syncthreads();
         for (int i = threadIdx.x; i < d; i += kLnThreads) {
-            atomicAdd(&dgamma[i], s_acc[i]);
-            atomicAdd(&dbeta[i], s_acc[d + i]);
+            if (dgamma != nullptr) {
+                atomicAdd(&dgamma[i], s_acc[i]);
+                atomicAdd(&dbeta[i], s_acc[d + i]);
+            }
+            if constexpr (COLSUM) atomicAdd(&dx_colsum[i], s_acc[2 * d + i]);
         }
     }
 }
@@ -284,8 +298,8 @@ extern "C" int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t 
 extern "C" int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t lddy, const void* x, int64_t ldx,
                                       const int32_t* row_index, const void* gamma, const float* mean,
                                       const float* rstd, const void* dres, int64_t lddres, void* dx, int64_t lddx,
-                                      float* dgamma, float* dbeta, int64_t rows, int64_t d, int x_dtype,
-                                      void* stream) {
+                                      float* dgamma, float* dbeta, float* dx_colsum, int64_t rows, int64_t d,
+                                      int x_dtype, void* stream) {
     B200_CHECK_CTX(ctx);
     B200_CHECK_ARG(dy && x && gamma && mean && rstd && dx, "layernorm_bwd: null pointer");
     B200_CHECK_ARG((dgamma == nullptr) == (dbeta == nullptr), "layernorm_bwd: dgamma/dbeta must come together");
@@ -295,22 +309,25 @@ extern "C" int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t
                    "layernorm_bwd: row pitches must be multiples of 8");
     const int wpb = kLnThreads / 32;
     const int64_t want = ceil_div(rows, wpb * 4);  // >= 4 rows per warp amortise the dgamma/dbeta atomics
-    const int grid = static_cast<int>(want < ctx->num_sms * 4 ? (want > 0 ? want : 1) : ctx->num_sms * 4);
-    const size_t smem = 2 * d * sizeof(float);
+    const int per_sm = d <= 768 ? 2 : 1;
+    const int grid = static_cast<int>(want < ctx->num_sms * per_sm ? (want > 0 ? want : 1) : ctx->num_sms * per_sm);
+    const size_t smem = 3 * d * sizeof(float);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     B200_CHECK_ARG(x_dtype == B200CLIP_DT_BF16 || x_dtype == B200CLIP_DT_F32, "layernorm_bwd: bad x dtype");
-#define CALL_T(NV, TX)                                                                                              \
-    layernorm_bwd_kernel<NV, TX><<<grid, kLnThreads, smem, st>>>(                                                   \
+#define CALL_T(NV, TX, CS)                                                                                          \
+    layernorm_bwd_kernel<NV, TX, CS><<<grid, kLnThreads, smem, st>>>(                                               \
         static_cast<const __nv_bfloat16*>(dy), lddy, static_cast<const TX*>(x), ldx, row_index,                    \
         static_cast<const __nv_bfloat16*>(gamma), mean, rstd, static_cast<const __nv_bfloat16*>(dres), lddres,     \
-        static_cast<__nv_bfloat16*>(dx), lddx, dgamma, dbeta, static_cast<int>(rows), static_cast<int>(d))
-#define CALL(NV)                                  \
-    do {                                          \
-        if (x_dtype == B200CLIP_DT_BF16) {        \
-            CALL_T(NV, __nv_bfloat16);            \
-        } else {                                  \
-            CALL_T(NV, float);                    \
-        }                                         \
+        static_cast<__nv_bfloat16*>(dx), lddx, dgamma, dbeta, dx_colsum, static_cast<int>(rows), static_cast<int>(d))
+#define CALL(NV)                                                       \
+    do {                                                               \
+        if (x_dtype == B200CLIP_DT_BF16) {                             \
+            if (dx_colsum) { CALL_T(NV, __nv_bfloat16, true); }        \
+            else { CALL_T(NV, __nv_bfloat16, false); }                 \
+        } else {                                                       \
+            if (dx_colsum) { CALL_T(NV, float, true); }                \
+            else { CALL_T(NV, float, false); }                         \
+        }                                                              \
     } while (0)
     LN_DISPATCH(d, CALL);
 #undef CALL

@@ -403,11 +403,11 @@ extern "C" int b200clip_clip_loss_bwd(b200clip_ctx* ctx, const float* img_all, c
     B200_CHECK_CUDA(cudaMemsetAsync(d_img, 0, sizeof(float) * Bl * E, st));
     B200_CHECK_CUDA(cudaMemsetAsync(d_txt, 0, sizeof(float) * Bl * E, st));
     if ((rc = b200clip_gemm_bf16(ctx, G, Bg, B200CLIP_MAJOR_K, txt_bf, E, B200CLIP_MAJOR_MN, d_img, E, B200CLIP_DT_F32,
-                                 nullptr, nullptr, 0, nullptr, coef, Bl, E, Bg, B200CLIP_EPI_NONE, 0, 1, stream)))
+                                 nullptr, nullptr, 0, nullptr, coef, nullptr, Bl, E, Bg, B200CLIP_EPI_NONE, 0, 1, stream)))
         return rc;
     if ((rc = b200clip_gemm_bf16(ctx, G + Bl * Bg, Bg, B200CLIP_MAJOR_K, img_bf, E, B200CLIP_MAJOR_MN, d_txt, E,
-                                 B200CLIP_DT_F32, nullptr, nullptr, 0, nullptr, coef, Bl, E, Bg, B200CLIP_EPI_NONE, 0, 1,
-                                 stream)))
+                                 B200CLIP_DT_F32, nullptr, nullptr, 0, nullptr, coef, nullptr, Bl, E, Bg, B200CLIP_EPI_NONE, 0,
+                                 1, stream)))
         return rc;
     return 0;
 }

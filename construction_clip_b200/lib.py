@@ -27,9 +27,9 @@ SIGNATURES = {
     "b200clip_launch_count": [],
     "b200clip_ctx_create": [C.POINTER(_p), _i],
     "b200clip_ctx_destroy": [_p],
-    "b200clip_gemm_bf16": [_p, _p, _l, _i, _p, _l, _i, _p, _l, _i, _p, _p, _l, _p, _p, _l, _l, _l, _i, _i, _i, _p],
+    "b200clip_gemm_bf16": [_p, _p, _l, _i, _p, _l, _i, _p, _l, _i, _p, _p, _l, _p, _p, _p, _l, _l, _l, _i, _i, _i, _p],
     "b200clip_layernorm_fwd": [_p, _p, _l, _p, _p, _p, _l, _p, _p, _p, _l, _p, _p, _p, _l, _l, _f, _i, _i, _p],
-    "b200clip_layernorm_bwd": [_p, _p, _l, _p, _l, _p, _p, _p, _p, _p, _l, _p, _l, _p, _p, _l, _l, _i, _p],
+    "b200clip_layernorm_bwd": [_p, _p, _l, _p, _l, _p, _p, _p, _p, _p, _l, _p, _l, _p, _p, _p, _l, _l, _i, _p],
     "b200clip_attn_fwd": [_p, _p, _p, _p, _l, _l, _l, _i, _p],
     "b200clip_attn_bwd": [_p, _p, _p, _p, _p, _p, _l, _l, _l, _i, _p],
     "b200clip_embed_tokens_fwd": [_p, _p, _p, _p, _p, _i, _p, _l, _l, _l, _l, _p],

@@ -43,7 +43,7 @@ def _row_major(t: torch.Tensor, name: str):
 GEMM_PROFILE = None
 
 
-def gemm(a, b, *, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, aux=None, preact=None, scale=None,
+def gemm(a, b, *, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, aux=None, preact=None, scale=None, colsum=None,
          epilogue=L.EPI_NONE, out=None, out_dtype=bf16, split_k=1, accumulate=False):
     """C[M,N] = sum_k A(m,k) B(n,k) (+bias) -> epilogue.  ``a``/``b`` are the STORED matrices:
     K-major operands are [rows, K]; MN-major operands are [K, rows]."""
@@ -73,7 +73,7 @@ def gemm(a, b, *, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, aux=None, pre
     L.check(L.load().b200clip_gemm_bf16(
         ctx, a.data_ptr(), lda, a_major, b.data_ptr(), ldb, b_major, out.data_ptr(), ldc,
         L.DT_F32 if out.dtype == f32 else L.DT_BF16, _ptr(bias), _ptr(aux),
-        _row_major(aux, "aux") if aux is not None else 0, _ptr(preact), _ptr(scale), M, N, K, epilogue,
+        _row_major(aux, "aux") if aux is not None else 0, _ptr(preact), _ptr(scale), _ptr(colsum), M, N, K, epilogue,
         split_k, 1 if accumulate else 0, st), "gemm_bf16")
     if prof is not None:
         e1.record()
@@ -86,9 +86,10 @@ def linear_fwd(x, w, bias=None, *, epilogue=L.EPI_NONE, aux=None, preact=None, o
     return gemm(x, w, bias=bias, aux=aux, preact=preact, epilogue=epilogue, out=out, out_dtype=out_dtype)
 
 
-def linear_dgrad(dy, w, *, epilogue=L.EPI_NONE, aux=None, out=None):
-    """dx = dy @ w   (w stored [N',K']; read as an MN-major B operand, no transpose copy)."""
-    return gemm(dy, w, b_major=L.MAJOR_MN, epilogue=epilogue, aux=aux, out=out)
+def linear_dgrad(dy, w, *, epilogue=L.EPI_NONE, aux=None, out=None, colsum=None):
+    """dx = dy @ w   (w stored [N',K']; read as an MN-major B operand, no transpose copy).
+    ``colsum`` (fp32 [K']) accumulates the column sums of dx."""
+    return gemm(dy, w, b_major=L.MAJOR_MN, epilogue=epilogue, aux=aux, out=out, colsum=colsum)
 
 
 def linear_wgrad(dy, x, out):
@@ -118,7 +119,7 @@ def layernorm_fwd(x, gamma, beta, *, rows=None, row_index=None, neg_row=None, ad
     return (out, mean, rstd) if want_stats else out
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, *, row_index=None, dres=None, dx=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, *, row_index=None, dres=None, dx=None, dx_colsum=None):
     rows, d = dy.shape
     if dx is None:
         dx = torch.empty((rows, d), device=dy.device, dtype=bf16)
@@ -127,7 +128,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, *, row_index=None, dr
         ctx, dy.data_ptr(), _row_major(dy, "dy"), x.data_ptr(), _row_major(x, "x"), _ptr(row_index),
         gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), _ptr(dres),
         _row_major(dres, "dres") if dres is not None else 0, dx.data_ptr(), _row_major(dx, "dx"),
-        _ptr(dgamma), _ptr(dbeta), rows, d, _dt(x), st), "layernorm_bwd")
+        _ptr(dgamma), _ptr(dbeta), _ptr(dx_colsum), rows, d, _dt(x), st), "layernorm_bwd")
     return dx
 
 

@@ -84,28 +84,33 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None):
 
 
 def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved):
+    """Bias gradients are column sums of the gradient stream; they are produced by the kernel that
+    WRITES each tensor (GEMM epilogue ``colsum`` / LayerNorm-backward ``dx_colsum``) instead of by
+    separate reduction passes -- only dqkv (written by the attention backward) and the incoming dy
+    of the last block use the stand-alone colsum kernel."""
+    O.colsum(dy, G[_blk(prefix, layers - 1) + "mlp.c_proj.bias"])
     for i in reversed(range(layers)):
         p = _blk(prefix, i)
         s: BlockSaved = saved.blocks[i]
         # ---- MLP branch: y = x2 + c_proj(gelu(c_fc(ln_2(x2))))
-        O.colsum(dy, G[p + "mlp.c_proj.bias"])
         O.linear_wgrad(dy, s.g, G[p + "mlp.c_proj.weight"])
-        df = O.linear_dgrad(dy, W[p + "mlp.c_proj.weight"], epilogue=L.EPI_QUICKGELU_BWD, aux=s.f)
-        O.colsum(df, G[p + "mlp.c_fc.bias"])
+        df = O.linear_dgrad(dy, W[p + "mlp.c_proj.weight"], epilogue=L.EPI_QUICKGELU_BWD, aux=s.f,
+                            colsum=G[p + "mlp.c_fc.bias"])
         O.linear_wgrad(df, s.h2, G[p + "mlp.c_fc.weight"])
         dh2 = O.linear_dgrad(df, W[p + "mlp.c_fc.weight"])
         dx2 = O.layernorm_bwd(dh2, s.x2, W[p + "ln_2.weight"], s.mean2, s.rstd2, G[p + "ln_2.weight"],
-                              G[p + "ln_2.bias"], dres=dy)
+                              G[p + "ln_2.bias"], dres=dy, dx_colsum=G[p + "attn.out_proj.bias"])
         # ---- attention branch: x2 = x + out_proj(attn(in_proj(ln_1(x))))
-        O.colsum(dx2, G[p + "attn.out_proj.bias"])
         O.linear_wgrad(dx2, s.a, G[p + "attn.out_proj.weight"])
         da = O.linear_dgrad(dx2, W[p + "attn.out_proj.weight"])
         dqkv = O.attn_bwd(s.qkv, s.a, s.lse, da, B, S, H, causal)
         O.colsum(dqkv, G[p + "attn.in_proj_bias"])
         O.linear_wgrad(dqkv, s.h1, G[p + "attn.in_proj_weight"])
         dh1 = O.linear_dgrad(dqkv, W[p + "attn.in_proj_weight"])
+        # dx of this LayerNorm is the dy of block i-1: its column sums are that block's c_proj bias gradient
+        prev_bias = G[_blk(prefix, i - 1) + "mlp.c_proj.bias"] if i > 0 else None
         dy = O.layernorm_bwd(dh1, s.x, W[p + "ln_1.weight"], s.mean1, s.rstd1, G[p + "ln_1.weight"],
-                             G[p + "ln_1.bias"], dres=dx2)
+                             G[p + "ln_1.bias"], dres=dx2, dx_colsum=prev_bias)
         saved.blocks[i] = None  # release this layer's activations
     return dy
 

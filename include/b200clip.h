@@ -83,14 +83,16 @@ int b200clip_ctx_destroy(b200clip_ctx* ctx);
  * except EPI_RESIDUAL with an fp32 C, where aux is fp32 too (the fp32 residual stream).
  * preact: bf16 [M,N] (ldc pitch) or NULL (EPI_QUICKGELU only).
  * scale: optional device fp32 scalar; acc is multiplied by it before bias (NULL = 1).
+ * colsum: optional fp32 [N]; the column sums of C (after the epilogue) are ACCUMULATED into it -- the
+ * bias gradient when C is a dgrad output (replaces a separate reduction pass over C).
  * split_k > 1 splits the reduction over `split_k` CTAs per tile and ACCUMULATES into C with
  * fp32 atomics (requires out_dtype F32, EPI_NONE, no bias; C must be pre-zeroed or hold a
  * value to accumulate onto).  split_k = 0 lets the library choose (only when out is F32).
  * accumulate != 0 with out F32 adds to C instead of overwriting (atomic). */
 int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda, int a_major, const void* B, int64_t ldb,
                        int b_major, void* C, int64_t ldc, int out_dtype, const void* bias, const void* aux,
-                       int64_t ldaux, void* preact, const float* scale, int64_t M, int64_t N, int64_t K,
-                       int epilogue, int split_k, int accumulate, void* stream);
+                       int64_t ldaux, void* preact, const float* scale, float* colsum, int64_t M, int64_t N,
+                       int64_t K, int epilogue, int split_k, int accumulate, void* stream);
 
 /* ---- clip.model.LayerNorm (fp32 statistics, eps, affine) ------------------------------------
  * y[r,:] = LN(x[src(r),:]) * gamma + beta ; src(r) = row_index ? row_index[r] : r.
@@ -108,11 +110,13 @@ int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t ldx, const 
                            int64_t rows, int64_t d, float eps, int x_dtype, int y_dtype, void* stream);
 /* dx[dst(r),:] = (dres ? dres[r,:] : 0) + LN'(dy[r,:]) ; dgamma/dbeta fp32 [d] ACCUMULATED (atomics).
  * x (x_dtype bf16 or f32) is read with the same src(r) mapping as the forward; dx is written at
- * dst(r) = src(r).  dy, dres, dx are bf16 (the gradient stream is bf16). */
+ * dst(r) = src(r).  dy, dres, dx are bf16 (the gradient stream is bf16).  dx_colsum: optional fp32 [d],
+ * ACCUMULATES the column sums of dx (the bias gradient of the Linear that produced this LayerNorm's
+ * input through the residual stream). */
 int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t lddy, const void* x, int64_t ldx,
                            const int32_t* row_index, const void* gamma, const float* mean, const float* rstd,
                            const void* dres, int64_t lddres, void* dx, int64_t lddx, float* dgamma, float* dbeta,
-                           int64_t rows, int64_t d, int x_dtype, void* stream);
+                           float* dx_colsum, int64_t rows, int64_t d, int x_dtype, void* stream);
 
 /* ---- nn.MultiheadAttention(need_weights=False) core: softmax(q k^T / 8 + mask) v, head_dim 64 ----
  * qkv: bf16 [B*S, 3*H*64] (the packed in_proj output: q | k | v, each head-major), out: bf16 [B*S, H*64].

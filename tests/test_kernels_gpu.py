@@ -85,7 +85,9 @@ def test_gemm_epilogues(ops):
            "residual fp32 stream")
     s = torch.sigmoid(1.702 * aux.float())
     gref = (a.float() @ w.float().t()) * (s * (1 + 1.702 * aux.float() * (1 - s)))
-    _close(ops.gemm(a, w, epilogue=L.EPI_QUICKGELU_BWD, aux=aux), gref, 3e-2, 1e-2, "quickgelu_bwd")
+    cs = torch.zeros(N, device="cuda")
+    _close(ops.gemm(a, w, epilogue=L.EPI_QUICKGELU_BWD, aux=aux, colsum=cs), gref, 3e-2, 1e-2, "quickgelu_bwd")
+    _close(cs, gref.sum(0), 0.5, 1e-2, "fused colsum of C")
     sc = torch.tensor([0.37], device="cuda")
     _close(ops.gemm(a, w, scale=sc, out_dtype=f32), 0.37 * (a.float() @ w.float().t()), 1e-3, 1e-3, "scale f32")
     # strided A (row pitch > K): the CLS-row gather pattern x[:, 0, :]
@@ -111,8 +113,10 @@ def test_layernorm(ops, rows, d):
     torch.nn.functional.layer_norm(xr, (d,), gr, br, 1e-5).backward(dy.float())
     dg = torch.zeros(d, device="cuda")
     db = torch.zeros(d, device="cuda")
-    dx = ops.layernorm_bwd(dy, x, g, mean, rstd, dg, db, dres=dres)
+    dcs = torch.zeros(d, device="cuda")
+    dx = ops.layernorm_bwd(dy, x, g, mean, rstd, dg, db, dres=dres, dx_colsum=dcs)
     _close(dx, xr.grad + dres.float(), 3e-2, 2e-2, "ln dx")
+    _close(dcs, (xr.grad + dres.float()).sum(0), 2e-2 * math.sqrt(rows), 1e-2, "ln dx colsum")
     # fp32 input (the residual stream) / fp32 output variants
     xf = torch.randn(rows, d, device="cuda") * 2
     y32, m32, r32 = ops.layernorm_fwd(xf, g, b, want_stats=True)
