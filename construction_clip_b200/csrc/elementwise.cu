@@ -297,7 +297,12 @@ __global__ void cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, f
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ master, __nv_bfloat16* __restrict__ param, const float* __restrict__ grad,
              float* __restrict__ m, float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
-             float wd, float grad_scale, float bc1, float bc2) {
+             float wd, float grad_scale, float bc1, float bc2, const float* __restrict__ hyper) {
+    if (hyper != nullptr) {  // step-dependent scalars from device memory (CUDA-graph replay)
+        lr = __ldg(hyper);
+        bc1 = __ldg(hyper + 1);
+        bc2 = __ldg(hyper + 2);
+    }
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
         const float g = grad[i] * grad_scale;
@@ -478,14 +483,14 @@ extern "C" int b200clip_cast_bf16_to_f32(b200clip_ctx* ctx, const void* src, flo
 
 extern "C" int b200clip_adamw(b200clip_ctx* ctx, float* master, void* param_bf16, const float* grad, float* m, float* v,
                               int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
-                              float grad_scale, int64_t step, void* stream) {
+                              float grad_scale, int64_t step, const float* hyper_dev, void* stream) {
     B200_CHECK_CTX(ctx);
-    B200_CHECK_ARG(master && grad && m && v && n > 0 && step > 0, "adamw: bad argument");
+    B200_CHECK_ARG(master && grad && m && v && n > 0 && (step > 0 || hyper_dev), "adamw: bad argument");
     const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
     const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
     adamw_kernel<<<grid_for(n, 256, ctx->num_sms, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         master, static_cast<__nv_bfloat16*>(param_bf16), grad, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale,
-        bc1, bc2);
+        bc1, bc2, hyper_dev);
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -284,8 +284,8 @@ def clip_loss_bwd(img_all, txt_all, logit_scale, lse_i_all, lse_t_all, grad_out,
     return d_img, d_txt, d_ls
 
 
-def adamw(master, param_bf16, grad, m, v, *, lr, beta1, beta2, eps, weight_decay, grad_scale, step):
+def adamw(master, param_bf16, grad, m, v, *, lr, beta1, beta2, eps, weight_decay, grad_scale, step, hyper=None):
     ctx, st = _ctx_stream(master)
     L.check(L.load().b200clip_adamw(ctx, master.data_ptr(), _ptr(param_bf16), grad.data_ptr(), m.data_ptr(),
                                     v.data_ptr(), master.numel(), lr, beta1, beta2, eps, weight_decay, grad_scale,
-                                    step, st), "adamw")
+                                    step, _ptr(hyper), st), "adamw")

@@ -200,10 +200,12 @@ int b200clip_clip_loss_bwd(b200clip_ctx* ctx, const float* img_all, const float*
                            void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---- AdamW step (CLIP/train.py:143,169) on flat buffers: fp32 master weights, bf16 shadow -------
- * p -= lr * (m_hat / (sqrt(v_hat) + eps) + wd * p);  grad fp32 (multiplied by grad_scale). */
+ * p -= lr * (m_hat / (sqrt(v_hat) + eps) + wd * p);  grad fp32 (multiplied by grad_scale).
+ * hyper_dev: optional DEVICE float[3] = {lr, 1 - beta1^step, 1 - beta2^step}; when non-NULL it overrides
+ * `lr` / `step`, so that a captured CUDA graph of the step can be replayed with a changing schedule. */
 int b200clip_adamw(b200clip_ctx* ctx, float* master, void* param_bf16, const float* grad, float* m, float* v,
                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
-                   int64_t step, void* stream);
+                   int64_t step, const float* hyper_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -232,3 +232,30 @@ def test_parse_coco_call_pattern():
         ref = orc.encode_image(img)
     assert cosine_rows(prefix.float(), ref).min() >= 0.999
     assert abs(similarity.sum() - 1) < 1e-3 and abs(similarity2.sum() - 1) < 1e-3
+
+
+def test_cuda_graph_step_matches_eager():
+    """The captured-and-replayed step (ClipTrainer.enable_cuda_graph) follows the same loss
+    trajectory and lands on the same weights as the eager step, with a changing learning rate."""
+    from construction_clip_b200.train import ClipTrainer
+    name, B = "tiny", 8
+    orc = oracle_model(name)
+    img, tok = _inputs(name, B, B, 12)
+    img2, tok2 = _inputs(name, B, B, 40)
+    batches = [(img.cuda(), tok.cuda().int()), (img2.cuda() * 0.5, tok2.cuda().int())]
+    runs = []
+    for use_graph in (False, True):
+        m = device_model(name, orc).train()
+        tr = ClipTrainer(m, lr=1e-3, warmup_steps=4, total_steps=20)
+        if use_graph:
+            tr.enable_cuda_graph()
+        losses = [tr.step(*batches[i % 2]).item() for i in range(6)]
+        runs.append((losses, tr.stores["visual"].w.float().clone(), tr.stores["text"].w.float().clone(),
+                     m.logit_scale.item(), tr.step_count))
+    (l0, wv0, wt0, ls0, c0), (l1, wv1, wt1, ls1, c1) = runs
+    assert c0 == c1 == 6
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (l0, l1)
+    # split-K fp32 atomics reorder sums between runs: weights agree to bf16 resolution, not bitwise
+    assert (wv0 - wv1).abs().max().item() <= 2e-2 and (wt0 - wt1).abs().max().item() <= 2e-2
+    assert abs(ls0 - ls1) < 1e-4

@@ -83,11 +83,26 @@ def main():
     same = torch.equal(w, w0)
     if not same:
         ok = False
+    # CUDA-graph replay of the whole sharded step (NCCL collectives captured) == eager
+    ga = gb = 0.0
+    if os.environ.get("DIST_GRAPH", "1") == "1":
+        res = []
+        for use_graph in (False, True):
+            mg = device_model(name, orc, device=dev).train()
+            tg = ClipTrainer(mg, lr=1e-4, warmup_steps=0)
+            if use_graph:
+                tg.enable_cuda_graph()
+            res.append([tg.step(img[sl].to(dev), tok[sl].to(dev).int()).item() for _ in range(4)])
+        ga, gb = res[0][-1], res[1][-1]
+        for a, b in zip(*res):
+            if abs(a - b) > 2e-3 * max(1.0, abs(a)):
+                ok = False
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print(f"DIST_CHECK world={world} Bg={Bg} loss_sharded={loss.item():.6f} loss_single={loss1.item():.6f} rel={rel:.2e} "
               f"worst_grad_cos={worst:.6f} dls_rel={dls:.2e} autograd_cos={c2:.6f} replicas_identical={same} "
+              f"graph_vs_eager_loss={gb:.5f}/{ga:.5f} "
               f"RESULT={'PASS' if flag.item() == 1.0 else 'FAIL'}", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() == 1.0 else 1)
