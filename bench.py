@@ -256,9 +256,21 @@ def run_ours(args):
     e2e_value = GLOBAL_BATCH * args.steps / (e2e_ms * 1e-3)
     _ = float(slot.item())
 
-    if rank != 0:
+    def shutdown():
+        # Drop captured graphs (they hold NCCL kernels) BEFORE the communicator goes away, and leave
+        # through os._exit: tearing down NCCL with live graph state has been seen to hang at exit.
+        trainer.enable_cuda_graph(False)
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         if world > 1:
-            dist.destroy_process_group()
+            dist.barrier()
+            sys.stdout.flush()
+            sys.stderr.flush()
+            os._exit(0)
+
+    if rank != 0:
+        shutdown()
         return
 
     peaks = load_peaks()
@@ -303,8 +315,7 @@ def run_ours(args):
         "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown()
 
 
 def main():

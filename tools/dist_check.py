@@ -93,6 +93,8 @@ def main():
             if use_graph:
                 tg.enable_cuda_graph()
             res.append([tg.step(img[sl].to(dev), tok[sl].to(dev).int()).item() for _ in range(4)])
+            tg.enable_cuda_graph(False)  # drop the captured graph before the communicator is torn down
+            del tg, mg
         ga, gb = res[0][-1], res[1][-1]
         for a, b in zip(*res):
             if abs(a - b) > 2e-3 * max(1.0, abs(a)):
@@ -104,8 +106,14 @@ def main():
               f"worst_grad_cos={worst:.6f} dls_rel={dls:.2e} autograd_cos={c2:.6f} replicas_identical={same} "
               f"graph_vs_eager_loss={gb:.5f}/{ga:.5f} "
               f"RESULT={'PASS' if flag.item() == 1.0 else 'FAIL'}", flush=True)
-    dist.destroy_process_group()
-    sys.exit(0 if flag.item() == 1.0 else 1)
+    code = 0 if flag.item() == 1.0 else 1
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(code)  # skip NCCL teardown (seen to hang after CUDA-graph capture of collectives)
 
 
 if __name__ == "__main__":
