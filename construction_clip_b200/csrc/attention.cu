@@ -61,14 +61,17 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
     const int S = p.S, H = p.H, npad = p.npad;
     const int TB = npad * 128;  // compact tile bytes
     constexpr int kAtoms = BIG ? 2 : 1;
-    uint8_t* sQ = smem;
+    // order [P atoms | Q | K | V]: the 128-row reads of the A operands (P, Q) spill into the NEXT tile,
+    // never past the allocation
+    uint8_t* sP = smem;  // kAtoms tiles of TB
+    uint8_t* sQ = sP + kAtoms * TB;
     uint8_t* sK = sQ + TB;
     uint8_t* sV = sK + TB;
-    uint8_t* sP = sV + TB;  // kAtoms tiles of TB
     constexpr int kTmemCols = BIG ? 128 : 64;
 
     const int warp = threadIdx.x >> 5;
     const int r = threadIdx.x;  // score row owned by this thread
+    const bool warp_live = warp * 32 < npad;  // warps whose 32 rows are all padding only take part in the barriers
 
     zero_smem(smem, (3 + kAtoms) * TB);
     if (threadIdx.x == 0) {
@@ -107,6 +110,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
                           make_smem_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
             umma_commit(&bar_mma);
         }
+        float sum = 1.f;
+        if (warp_live) {
         mbar_wait(&bar_mma, 0u);
         __syncwarp();
         tc_fence_after();
@@ -121,7 +126,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
             for (int j = 0; j < 16; ++j)
                 if (!masked(r, c0 + j, S, p.causal)) mx = fmaxf(mx, __uint_as_float(v[j]));
         }
-        float sum = 0.f;
+        sum = 0.f;
         for (int c0 = 0; c0 < npad; c0 += 16) {
             uint32_t v[16];
             tmem_ld_32x16(trow + c0, v);
@@ -141,6 +146,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
         }
         if (p.lse != nullptr && r < S)  // log2-domain: p = exp2(s * sc - lse)
             p.lse[(static_cast<int64_t>(b) * H + h) * S + r] = mx * sc + log2f(sum);
+        }  // warp_live
         fence_proxy_async_smem();
         tc_fence_before();
         __syncthreads();
@@ -152,10 +158,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
                           make_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
             umma_commit(&bar_mma);
         }
-        mbar_wait(&bar_mma, 1u);
-        __syncwarp();
-        tc_fence_after();
-        {
+        if (warp_live) {
+            mbar_wait(&bar_mma, 1u);
+            __syncwarp();
+            tc_fence_after();
             const float inv = 1.0f / sum;
             __nv_bfloat16* dst = p.out + (static_cast<int64_t>(b) * S + r) * d + h * 64;
 #pragma unroll
@@ -201,18 +207,20 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int S = p.S, H = p.H, npad = p.npad;
     const int TB = npad * 128;
     constexpr int kAtoms = BIG ? 2 : 1;
-    uint8_t* sQ = smem;
+    // order [P | dS | Q | dO | K | V]: 128-row A-operand reads (dS, Q, dO) spill into the next tile only
+    uint8_t* sP = smem;
+    uint8_t* sdS = sP + kAtoms * TB;
+    uint8_t* sQ = sdS + kAtoms * TB;
     uint8_t* sdO = sQ + TB;
     uint8_t* sK = sdO + TB;
     uint8_t* sV = sK + TB;
-    uint8_t* sP = sV + TB;
-    uint8_t* sdS = sP + kAtoms * TB;
     constexpr int kTmemCols = 256;
     // TMEM columns: [0,128) S, later dV [0,64) + dK [64,128);  [128,256) dP, later dQ [128,192)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int r = (warp & 3) * 32 + lane;  // score row (TMEM lane) of this thread
     const int half = warp >> 2;            // which share of the columns / output chunks it takes
+    const bool warp_live = (warp & 3) * 32 < npad;  // all-padding warps only take part in the barriers
 
     zero_smem(smem, (4 + 2 * kAtoms) * TB);
     if (threadIdx.x == 0) {
@@ -260,8 +268,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 #pragma unroll
             for (int c = 0; c < 8; ++c) ov[c] = __ldg(op + c);
         }
-        mbar_wait(&bar_load, it & 1u);
         if (threadIdx.x == 0) {
+            mbar_wait(&bar_load, it & 1u);
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -273,49 +281,52 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                           make_smem_desc_sw128(smem_u32(sV) + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
             umma_commit(&bar_mma);
         }
-        // D = rowsum(dO o O) while the tensor core works
-        float D = 0.f;
-        if (live) {
+        if (warp_live) {
+            // D = rowsum(dO o O) while the tensor core works
+            mbar_wait(&bar_load, it & 1u);
+            float D = 0.f;
+            if (live) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const uint4 dv = *reinterpret_cast<const uint4*>(sdO + r * 128 + ((c ^ (r & 7)) << 4));
-                const uint32_t a[4] = {dv.x, dv.y, dv.z, dv.w}, o4[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w};
+                for (int c = 0; c < 8; ++c) {
+                    const uint4 dv = *reinterpret_cast<const uint4*>(sdO + r * 128 + ((c ^ (r & 7)) << 4));
+                    const uint32_t a[4] = {dv.x, dv.y, dv.z, dv.w}, o4[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float2 x = unpack_bf16(a[j]), y = unpack_bf16(o4[j]);
-                    D = fmaf(x.x, y.x, D);
-                    D = fmaf(x.y, y.y, D);
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 x = unpack_bf16(a[j]), y = unpack_bf16(o4[j]);
+                        D = fmaf(x.x, y.x, D);
+                        D = fmaf(x.y, y.y, D);
+                    }
                 }
             }
-        }
-        mbar_wait(&bar_mma, 0u);
-        __syncwarp();
-        tc_fence_after();
+            mbar_wait(&bar_mma, 0u);
+            __syncwarp();
+            tc_fence_after();
 
-        // single pass: P = exp2(S*sc - lse), dS = P o (dP - D) / 8 -> swizzled smem (bf16)
-        for (int ci = ch0; ci < ch1; ++ci) {
-            const int c0 = ci << 4;
-            uint32_t v[16], g[16];
-            tmem_ld_32x16(trow + c0, v);
-            tmem_ld_32x16(trow + 128 + c0, g);
-            tmem_ld_wait();
-            float pe[16], ds[16];
+            // single pass: P = exp2(S*sc - lse), dS = P o (dP - D) / 8 -> swizzled smem (bf16)
+            for (int ci = ch0; ci < ch1; ++ci) {
+                const int c0 = ci << 4;
+                uint32_t v[16], g[16];
+                tmem_ld_32x16(trow + c0, v);
+                tmem_ld_32x16(trow + 128 + c0, g);
+                tmem_ld_wait();
+                float pe[16], ds[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                const bool m = !live || masked(r, c0 + j, S, p.causal);
-                const float e = m ? 0.f : exp2f(__uint_as_float(v[j]) * sc - m2);
-                pe[j] = e;
-                ds[j] = m ? 0.f : e * (__uint_as_float(g[j]) - D) * 0.125f;
-            }
-            if (r < npad) {
-                *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, c0 >> 3)) =
-                    make_uint4(pack_bf16(pe[0], pe[1]), pack_bf16(pe[2], pe[3]), pack_bf16(pe[4], pe[5]), pack_bf16(pe[6], pe[7]));
-                *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, (c0 >> 3) + 1)) =
-                    make_uint4(pack_bf16(pe[8], pe[9]), pack_bf16(pe[10], pe[11]), pack_bf16(pe[12], pe[13]), pack_bf16(pe[14], pe[15]));
-                *reinterpret_cast<uint4*>(p_chunk(sdS, TB, r, c0 >> 3)) =
-                    make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
-                *reinterpret_cast<uint4*>(p_chunk(sdS, TB, r, (c0 >> 3) + 1)) =
-                    make_uint4(pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]), pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
+                for (int j = 0; j < 16; ++j) {
+                    const bool m = !live || masked(r, c0 + j, S, p.causal);
+                    const float e = m ? 0.f : exp2f(__uint_as_float(v[j]) * sc - m2);
+                    pe[j] = e;
+                    ds[j] = m ? 0.f : e * (__uint_as_float(g[j]) - D) * 0.125f;
+                }
+                if (r < npad) {
+                    *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, c0 >> 3)) =
+                        make_uint4(pack_bf16(pe[0], pe[1]), pack_bf16(pe[2], pe[3]), pack_bf16(pe[4], pe[5]), pack_bf16(pe[6], pe[7]));
+                    *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, (c0 >> 3) + 1)) =
+                        make_uint4(pack_bf16(pe[8], pe[9]), pack_bf16(pe[10], pe[11]), pack_bf16(pe[12], pe[13]), pack_bf16(pe[14], pe[15]));
+                    *reinterpret_cast<uint4*>(p_chunk(sdS, TB, r, c0 >> 3)) =
+                        make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+                    *reinterpret_cast<uint4*>(p_chunk(sdS, TB, r, (c0 >> 3) + 1)) =
+                        make_uint4(pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]), pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
+                }
             }
         }
         fence_proxy_async_smem();
@@ -341,10 +352,10 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             }
             umma_commit(&bar_mma);
         }
-        mbar_wait(&bar_mma, 1u);
-        __syncwarp();
-        tc_fence_after();
-        {
+        if (warp_live) {
+            mbar_wait(&bar_mma, 1u);
+            __syncwarp();
+            tc_fence_after();
             // six 32-column output chunks per row: dQ (TMEM 128..191), dK (64..127), dV (0..63);
             // the two threads of a row take three each
             __nv_bfloat16* dst = p.out + (static_cast<int64_t>(b) * S + r) * (3 * d) + h * 64;
@@ -379,9 +390,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     }
 }
 
-// dynamic shared memory: compact tiles + room for the M=128 over-read of the last A tile + alignment
-static int fwd_smem(bool big, int npad) { return (3 + (big ? 2 : 1)) * npad * 128 + (kTile - npad * 128) + 1024; }
-static int bwd_smem(bool big, int npad) { return (4 + 2 * (big ? 2 : 1)) * npad * 128 + (kTile - npad * 128) + 1024; }
+// dynamic shared memory: compact tiles (A operands first, so their 128-row reads stay inside) + alignment.
+// The last A tile (Q fwd / dO bwd) is followed by >= 2 more tiles of npad >= 16 rows... not enough when
+// npad < 43: keep the allocation at least kTile past the start of that tile.
+static int fwd_smem(bool big, int npad) {
+    const int tb = npad * 128, atoms = big ? 2 : 1;
+    const int need = atoms * tb + kTile;  // Q starts after the P atoms and is read for 128 rows
+    const int have = (3 + atoms) * tb;
+    return (have > need ? have : need) + 1024;
+}
+static int bwd_smem(bool big, int npad) {
+    const int tb = npad * 128, atoms = big ? 2 : 1;
+    const int need = (2 * atoms + 1) * tb + kTile;  // dO starts after P, dS, Q and is read for 128 rows
+    const int have = (4 + 2 * atoms) * tb;
+    return (have > need ? have : need) + 1024;
+}
 
 int init_attention(b200clip_ctx*) {
     cudaError_t e;
