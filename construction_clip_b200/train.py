@@ -142,6 +142,8 @@ class ClipTrainer:
         self.ls_m = torch.zeros(1, device=self.device, dtype=f32)
         self.ls_v = torch.zeros(1, device=self.device, dtype=f32)
         self.last_correct = None
+        self.two_streams = True
+        self._tower_streams = None
         # CUDA-graph mode (enable_cuda_graph): step-dependent scalars live in device memory
         self._use_graph = False
         self._graph = None
@@ -169,22 +171,55 @@ class ClipTrainer:
         return self.lr
 
     def forward_backward(self, image, text):
-        """Fills the flat gradient buffers with d(global loss)/d(params); returns the loss tensor."""
+        """Fills the flat gradient buffers with d(global loss)/d(params); returns the loss tensor.
+
+        The two towers are independent until the loss, so they run on two CUDA streams: whenever a
+        persistent GEMM of one tower leaves SMs idle in its last (partial) wave, CTAs of the other
+        tower's kernel fill them -- at 128 pairs / GPU most GEMMs are 1.0x .. 4.1x waves of tiles."""
         cfg = self.cfg
+        dev = self.device
         for k in self.grads:
             self.grads[k].zero_()
         Wv, Wt = self.stores["visual"].W, self.stores["text"].W
-        img_f, saved_i = T.vision_fwd(Wv, cfg, image, True)
-        txt_f, saved_t = T.text_fwd(Wt, cfg, text, True)
+        two = self.two_streams and dev.type == "cuda"
+        main = torch.cuda.current_stream(dev)
+        if two:
+            if self._tower_streams is None:
+                self._tower_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            sv, stt = self._tower_streams
+            sv.wait_stream(main)
+            stt.wait_stream(main)
+        else:
+            sv = stt = main
+        with torch.cuda.stream(sv):
+            img_f, saved_i = T.vision_fwd(Wv, cfg, image, True)
+        with torch.cuda.stream(stt):
+            txt_f, saved_t = T.text_fwd(Wt, cfg, text, True)
+        if two:
+            main.wait_stream(sv)
+            main.wait_stream(stt)
+            img_f.record_stream(main)
+            txt_f.record_stream(main)
         st = _LossState(img_f, txt_f, self.ls_master, self.group)
         d_img, d_txt, d_ls = st.backward(None)
+        if two:
+            sv.wait_stream(main)
+            stt.wait_stream(main)
+            d_img.record_stream(sv)
+            d_txt.record_stream(stt)
         work = []
-        T.vision_bwd(Wv, self.G["visual"], cfg, saved_i, d_img)
+        with torch.cuda.stream(sv):
+            T.vision_bwd(Wv, self.G["visual"], cfg, saved_i, d_img)
+            if self.world > 1:
+                work.append(dist.all_reduce(self.grads["visual"], group=self.group, async_op=True))
+        with torch.cuda.stream(stt):
+            T.text_bwd(Wt, self.G["text"], cfg, saved_t, d_txt)
+            if self.world > 1:
+                work.append(dist.all_reduce(self.grads["text"], group=self.group, async_op=True))
+        if two:
+            main.wait_stream(sv)
+            main.wait_stream(stt)
         if self.world > 1:
-            work.append(dist.all_reduce(self.grads["visual"], group=self.group, async_op=True))
-        T.text_bwd(Wt, self.G["text"], cfg, saved_t, d_txt)
-        if self.world > 1:
-            work.append(dist.all_reduce(self.grads["text"], group=self.group, async_op=True))
             work.append(dist.all_reduce(d_ls, group=self.group, async_op=True))
             for w in work:
                 w.wait()
