@@ -1,4 +1,5 @@
-// Fused multi-head attention (head_dim 64, sequence <= 128 = one tile) on tcgen05 tensor cores.
+// Fused multi-head attention (head_dim 64) on tcgen05 tensor cores: single-tile kernels for
+// sequences <= 128 (forward + backward), a KV-streaming forward for longer sequences.
 // Replaces the core of nn.MultiheadAttention(need_weights=False, attn_mask=causal|None) inside
 // clip.model.ResidualAttentionBlock.attention: softmax(q k^T / sqrt(64) + mask) v
 // (vision tower: S = 50, full; text tower: S = 77, causal with upstream's mask that does NOT
@@ -185,6 +186,160 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem, kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward for sequences longer than one tile (ViT-B/16: 197, ViT-L/14: 257, ViT-L/14@336: 577 tokens):
+// one CTA per (sample, head, 128-row query block), KV streamed in 128-row blocks with the online
+// softmax recurrence; S_j = Q K_j^T and P_j V_j run on the tensor core, the running output lives in
+// registers (64 fp32 per thread = one row) and is rescaled by exp2(m_old - m_new) per block.
+__global__ void __launch_bounds__(kAttnThreads)
+attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_q, bar_kv, bar_mma;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sQ = smem;
+    uint8_t* sK = sQ + kTile;
+    uint8_t* sV = sK + kTile;
+    uint8_t* sP = sV + kTile;  // two 64-column tiles
+    constexpr int kTmemCols = 256;  // [0,128) scores, [128,192) P V
+
+    const int warp = threadIdx.x >> 5;
+    const int r = threadIdx.x;
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tm_qkv);
+        mbar_init(&bar_q, 1);
+        mbar_init(&bar_kv, 1);
+        mbar_init(&bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+
+    const int S = p.S, H = p.H;
+    const int d = H * 64;
+    const int nqb = (S + 127) / 128;
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
+    const float sc = 0.125f * kLog2e;
+    const int num_work = p.B * H * nqb;
+    uint32_t it = 0, kv_it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+        const int qb = w % nqb;
+        const int bh = w / nqb;
+        const int b = bh / H, h = bh % H;
+        const int q0 = qb * 128;
+        const int row = q0 + r;  // query index inside the sample
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&bar_q, kTile);
+            tma_load_2d(sQ, &tm_qkv, &bar_q, h * 64, b * S + q0);
+        }
+        float m = -INFINITY, l = 0.f;
+        float o[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) o[c] = 0.f;
+        const int kv_end = p.causal ? min(S, q0 + 128) : S;
+        for (int k0 = 0; k0 < kv_end; k0 += 128, ++kv_it) {
+            if (threadIdx.x == 0) {
+                mbar_arrive_expect_tx(&bar_kv, 2 * kTile);
+                tma_load_2d(sK, &tm_qkv, &bar_kv, d + h * 64, b * S + k0);
+                tma_load_2d(sV, &tm_qkv, &bar_kv, 2 * d + h * 64, b * S + k0);
+                if (k0 == 0) mbar_wait(&bar_q, it & 1u);
+                mbar_wait(&bar_kv, kv_it & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem, make_smem_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024),
+                              make_smem_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, 0u);
+            __syncwarp();
+            tc_fence_after();
+            float mx = m;
+            for (int c0 = 0; c0 < 128; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld_32x16(trow + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = k0 + c0 + j;
+                    if (col < S && !(p.causal && col > row)) mx = fmaxf(mx, __uint_as_float(v[j]));
+                }
+            }
+            // a fully masked row (padding rows past S when causal) keeps mx = -inf: use 0 to stay finite
+            const float mref = (mx == -INFINITY) ? 0.f : mx;
+            const float alpha = exp2f((m - mref) * sc);  // m = -inf -> 0
+            float sum = 0.f;
+            for (int c0 = 0; c0 < 128; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld_32x16(trow + c0, v);
+                tmem_ld_wait();
+                float e[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = k0 + c0 + j;
+                    const bool msk = col >= S || (p.causal && col > row);
+                    e[j] = msk ? 0.f : exp2f((__uint_as_float(v[j]) - mref) * sc);
+                    sum += e[j];
+                }
+                *reinterpret_cast<uint4*>(p_chunk(sP, kTile, r, c0 >> 3)) =
+                    make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+                *reinterpret_cast<uint4*>(p_chunk(sP, kTile, r, (c0 >> 3) + 1)) =
+                    make_uint4(pack_bf16(e[8], e[9]), pack_bf16(e[10], e[11]), pack_bf16(e[12], e[13]), pack_bf16(e[14], e[15]));
+            }
+            l = l * alpha + sum;
+            m = mx;
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tmem + 128, make_smem_desc_sw128(smem_u32(sP) + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
+                              make_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
+                umma_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, 1u);
+            __syncwarp();
+            tc_fence_after();
+#pragma unroll
+            for (int c0 = 0; c0 < 64; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32(trow + 128 + c0, v);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) o[c0 + j] = fmaf(o[c0 + j], alpha, __uint_as_float(v[j]));
+            }
+            tc_fence_before();
+            __syncthreads();  // K / V / P and both accumulators are reused by the next block
+            tc_fence_after();
+        }
+        if (row < S) {
+            const float inv = 1.0f / l;
+            __nv_bfloat16* dst = p.out + (static_cast<int64_t>(b) * S + row) * d + h * 64;
+#pragma unroll
+            for (int j = 0; j < 64; j += 8) {
+                uint4 ov;
+                ov.x = pack_bf16(o[j] * inv, o[j + 1] * inv);
+                ov.y = pack_bf16(o[j + 2] * inv, o[j + 3] * inv);
+                ov.z = pack_bf16(o[j + 4] * inv, o[j + 5] * inv);
+                ov.w = pack_bf16(o[j + 6] * inv, o[j + 7] * inv);
+                *reinterpret_cast<uint4*>(dst + j) = ov;
+            }
+            if (p.lse != nullptr) p.lse[(static_cast<int64_t>(b) * H + h) * S + row] = m * sc + log2f(l);
+        }
     }
     if (warp == 0) {
         __syncwarp();
@@ -412,6 +567,8 @@ int init_attention(b200clip_ctx*) {
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(true, 128));
     if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_fwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * kTile + 1024);
+    if (e == cudaSuccess)
         e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem(false, 64));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem(true, 128));
@@ -422,12 +579,14 @@ int init_attention(b200clip_ctx*) {
     return 0;
 }
 
-static int check_attn_args(b200clip_ctx* ctx, const void* a, const void* b, int64_t B, int64_t S, int64_t H) {
+static int check_attn_args(b200clip_ctx* ctx, const void* a, const void* b, int64_t B, int64_t S, int64_t H,
+                           bool allow_long) {
     B200_CHECK_CTX(ctx);
     B200_CHECK_ARG(a && b, "attention: null pointer");
     B200_CHECK_ARG(B > 0 && H > 0 && S > 0, "attention: bad shape");
-    if (S > 128) {
-        set_error("attention: S=%lld > 128 needs the multi-tile kernel (not in this version)", (long long)S);
+    if (S > 128 && !allow_long) {
+        set_error("attention backward: S=%lld > 128 needs the multi-tile backward kernel (not in this version)",
+                  (long long)S);
         return B200CLIP_ERR_UNSUPPORTED;
     }
     B200_CHECK_ARG(B * S < (1ll << 31) && B * H < (1ll << 31), "attention: extent too large");
@@ -448,9 +607,27 @@ static int ctas_per_sm(int smem_bytes, int tmem_cols, int cap) {
 
 extern "C" int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, float* lse, int64_t B, int64_t S,
                                  int64_t H, int causal, void* stream) {
-    int rc = check_attn_args(ctx, qkv, out, B, S, H);
+    int rc = check_attn_args(ctx, qkv, out, B, S, H, true);
     if (rc) return rc;
     B200_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "attention: out not 16-byte aligned");
+    if (S > 128) {
+        CUtensorMap tml;
+        if ((rc = make_tmap_bf16_2d(ctx, &tml, qkv, 3 * H * 64, B * S, 3 * H * 64, 64, 128))) return rc;
+        AttnParams pl{};
+        pl.out = static_cast<__nv_bfloat16*>(out);
+        pl.lse = lse;
+        pl.B = static_cast<int>(B);
+        pl.S = static_cast<int>(S);
+        pl.H = static_cast<int>(H);
+        pl.causal = causal ? 1 : 0;
+        pl.npad = 128;
+        const int64_t work_l = B * H * ((S + 127) / 128);
+        B200_CHECK_ARG(work_l < (1ll << 31), "attention: extent too large");
+        const int grid_l = static_cast<int>(work_l < ctx->num_sms * 2 ? work_l : ctx->num_sms * 2);
+        attn_fwd_long_kernel<<<grid_l, kAttnThreads, 5 * kTile + 1024, static_cast<cudaStream_t>(stream)>>>(tml, pl);
+        B200_LAUNCH_CHECK();
+        return 0;
+    }
     CUtensorMap tm;
     if ((rc = make_tmap_bf16_2d(ctx, &tm, qkv, 3 * H * 64, B * S, 3 * H * 64, 64, static_cast<uint32_t>(S)))) return rc;
     AttnParams p{};
@@ -478,7 +655,7 @@ extern "C" int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, 
 extern "C" int b200clip_attn_bwd(b200clip_ctx* ctx, const void* qkv, const void* out, const float* lse,
                                  const void* dout, void* dqkv, int64_t B, int64_t S, int64_t H, int causal,
                                  void* stream) {
-    int rc = check_attn_args(ctx, qkv, dout, B, S, H);
+    int rc = check_attn_args(ctx, qkv, dout, B, S, H, false);
     if (rc) return rc;
     B200_CHECK_ARG(out && lse, "attention bwd: needs the forward's out and lse");
     B200_CHECK_ARG(dqkv && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,

@@ -121,7 +121,9 @@ int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t lddy, cons
 /* ---- nn.MultiheadAttention(need_weights=False) core: softmax(q k^T / 8 + mask) v, head_dim 64 ----
  * qkv: bf16 [B*S, 3*H*64] (the packed in_proj output: q | k | v, each head-major), out: bf16 [B*S, H*64].
  * causal != 0 applies upstream's build_attention_mask (-inf strictly above the diagonal; padding is
- * NOT masked).  S <= 128 (single tile) in this version. */
+ * NOT masked).  S <= 128 runs the single-tile kernel; longer sequences (ViT-B/16, ViT-L/14) stream the
+ * keys/values in 128-row blocks (forward only: b200clip_attn_bwd returns B200CLIP_ERR_UNSUPPORTED for
+ * S > 128 in this version). */
 int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H,
                       int causal, void* stream);
 /* dqkv: bf16 [B*S, 3*H*64].  `out` and `lse` are the forward's results (lse: fp32 [B*H*S], the row

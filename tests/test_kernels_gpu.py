@@ -178,6 +178,21 @@ def test_attention_fwd_bwd(ops, B, S, H, causal):
     _close(dqkv, qr.grad, 4e-2, 4e-2, "attn bwd")
 
 
+@pytest.mark.parametrize("B,S,H,causal", [(2, 197, 12, False), (1, 257, 16, False), (1, 577, 4, False), (2, 200, 2, True),
+                                          (3, 129, 1, False)])
+def test_attention_fwd_long(ops, B, S, H, causal):
+    """KV-streaming forward (ViT-B/16: 197 tokens, ViT-L/14: 257, ViT-L/14@336px: 577)."""
+    qkv = _rand((B * S, 3 * H * 64), 1.5, seed=S)
+    out, lse = ops.attn_fwd(qkv, B, S, H, causal, want_lse=True)
+    ref = _attn_ref(qkv, B, S, H, causal)
+    _close(out, ref, 2e-2, 2e-2, "attn fwd long")
+    q, k, _ = qkv.float().view(B, S, 3, H, 64).permute(2, 0, 3, 1, 4)
+    sc = q @ k.transpose(-1, -2) / 8.0
+    if causal:
+        sc = sc + torch.full((S, S), float("-inf"), device="cuda").triu_(1)
+    _close(lse.view(B, H, S), torch.logsumexp(sc, -1) * 1.4426950408889634, 2e-3, 1e-3, "lse (log2)")
+
+
 def test_embed_tokens(ops):
     B, S, d, V = 9, 77, 512, 49408
     g = torch.Generator(device="cuda").manual_seed(0)

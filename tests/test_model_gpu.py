@@ -259,3 +259,19 @@ def test_cuda_graph_step_matches_eager():
     # split-K fp32 atomics reorder sums between runs: weights agree to bf16 resolution, not bitwise
     assert (wv0 - wv1).abs().max().item() <= 2e-2 and (wt0 - wt1).abs().max().item() <= 2e-2
     assert abs(ls0 - ls1) < 1e-4
+
+
+def test_forward_vitb16_long_sequence():
+    """BASELINE config 3 model (ViT-B/16, 197 vision tokens): encode_image through the KV-streaming
+    attention forward."""
+    from oracle import clip_oracle as O
+    name = "ViT-B/16"
+    orc = oracle_model(name)
+    img = O.synth_images(3, 224, seed=SEED)
+    with torch.no_grad():
+        ref = orc.encode_image(img)
+    m = device_model(name, orc).eval()
+    with torch.no_grad():
+        got = m.encode_image(img.cuda())
+    assert got.shape == (3, 512)
+    assert cosine_rows(got.float().cpu(), ref).min() >= 0.999
