@@ -275,3 +275,23 @@ def test_forward_vitb16_long_sequence():
         got = m.encode_image(img.cuda())
     assert got.shape == (3, 512)
     assert cosine_rows(got.float().cpu(), ref).min() >= 0.999
+
+
+def test_forward_vitl14_padded_patch_embed():
+    """ViT-L/14 (BASELINE config 4 model): 257 tokens, width 1024 / 16 heads, and a 14x14 patch whose
+    im2col row (588) is zero-padded to 640 so that TMA's 16-byte pitch rule holds."""
+    from oracle import clip_oracle as O
+    name = "ViT-L/14"
+    orc = oracle_model(name)
+    img = O.synth_images(2, 224, seed=SEED)
+    tok = O.synth_tokens(2, seed=SEED, min_len=3, max_len=30)
+    with torch.no_grad():
+        lpi_ref, _ = orc(img, tok)
+        fi_ref = orc.encode_image(img)
+    m = device_model(name, orc).eval()
+    with torch.no_grad():
+        lpi, _ = m(img.cuda(), tok.cuda())
+        fi = m.encode_image(img.cuda())
+    assert fi.shape == (2, 768)
+    assert cosine_rows(fi.float().cpu(), fi_ref).min() >= 0.999
+    assert (lpi.float().cpu() - lpi_ref).abs().max().item() <= LOGIT_TOL
