@@ -13,6 +13,8 @@
 //              half of the tile's columns, transposing through shared memory so that every global
 //              access (aux load, C store) is a full 128-byte row segment
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty pair (MMA <-> epilogue).
+#include <type_traits>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -67,11 +69,15 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-// x * sigmoid(1.702 x) with ex2.approx + rcp.approx (relative error ~1e-6).  The FORWARD uses this
-// accurate form: tanh.approx (2^-11) measurably eats into the 1e-2 logit tolerance; the backward's
-// QuickGELU' below can afford it.
+// x * sigmoid(1.702 x) = x * rcp(1 + 2^(-1.702 log2(e) x)) with ex2.approx / rcp.approx: 5 instructions,
+// no range-check branches (the CUDA __fdividef / __expf pair costs ~3x as many), relative error
+// ~1e-6.  The FORWARD uses this accurate form -- tanh.approx (2^-11) measurably eats into the 1e-2
+// logit tolerance; the backward's QuickGELU' below can afford it.  x -> -inf gives x * 0, x -> +inf gives x.
 __device__ __forceinline__ float qgelu_fast(float x) {
-    return __fdividef(x, 1.0f + __expf(-1.702f * x));
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.4554669595930157f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    return x * r;
 }
 // acc * d/dx[x sigmoid(1.702x)] = 0.5 acc (1 + t + u (1 - t^2)), u = 0.851 x, t = tanh(u)   (6 instr.)
 __device__ __forceinline__ float qgelu_bwd_fast(float acc, float x) {
@@ -131,6 +137,7 @@ template <int EPI, bool OUT_F32, bool ATOMIC>
 __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOperands<EPI, OUT_F32>& op, uint32_t taddr,
                                                int m_base, int col0, float scale, uint8_t* stg, int lane) {
     using Op = EpiOperands<EPI, OUT_F32>;
+    using OutT = typename std::conditional<OUT_F32, float, __nv_bfloat16>::type;
     const int rrow = lane >> 3, rch = lane & 7;
     const int col = col0 + rch * 4;
     const bool col_ok = col < p.N;
@@ -142,20 +149,23 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
     for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) = make_uint4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
     __syncwarp();
-    // ---- coalesced layout: maths + stores
-    float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
+    // ---- coalesced layout: maths + stores.  Row pointers advance by a constant stride (no per-row
+    // 64-bit multiply); rows_left turns the row bound into a compare against the unrolled index.
+    const int64_t first = static_cast<int64_t>(m_base + rrow) * p.ldc + col;
+    OutT* cptr = reinterpret_cast<OutT*>(p.C) + first;
+    [[maybe_unused]] __nv_bfloat16* pptr = (EPI == B200CLIP_EPI_QUICKGELU && p.preact != nullptr) ? p.preact + first : nullptr;
+    const int64_t rstride = 4 * p.ldc;
+    const int rows_left = col_ok ? (p.M - m_base - rrow + 3) >> 2 : 0;  // number of valid i (rows m_base+rrow+4i < M)
+    [[maybe_unused]] float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int row = 4 * i + rrow;
-        const int grow = m_base + row;
         const uint4 v = *reinterpret_cast<const uint4*>(stg + stage_off(row, rch));
         float x0 = fmaf(__uint_as_float(v.x), scale, op.b0), x1 = fmaf(__uint_as_float(v.y), scale, op.b1);
         float x2 = fmaf(__uint_as_float(v.z), scale, op.b2), x3 = fmaf(__uint_as_float(v.w), scale, op.b3);
-        const bool ok = col_ok && grow < p.M;
+        const bool ok = i < rows_left;
         if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
-            if (p.preact != nullptr && ok)
-                *reinterpret_cast<uint2*>(p.preact + static_cast<int64_t>(grow) * p.ldc + col) =
-                    make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+            if (pptr != nullptr && ok) *reinterpret_cast<uint2*>(pptr) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
             x0 = qgelu_fast(x0); x1 = qgelu_fast(x1); x2 = qgelu_fast(x2); x3 = qgelu_fast(x3);
         } else if constexpr (Op::AUX_F32) {
             x0 += __uint_as_float(op.auxf[i].x); x1 += __uint_as_float(op.auxf[i].y);
@@ -170,26 +180,32 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
             }
         }
         if (ok) {
-            cs0 += x0; cs1 += x1; cs2 += x2; cs3 += x3;
+            if constexpr (EPI == B200CLIP_EPI_QUICKGELU_BWD) {  // the only flavour that carries a fused column sum
+                cs0 += x0; cs1 += x1; cs2 += x2; cs3 += x3;
+            }
             if constexpr (OUT_F32) {
-                float* dst = reinterpret_cast<float*>(p.C) + static_cast<int64_t>(grow) * p.ldc + col;
                 if constexpr (ATOMIC)
-                    red_add_v4(dst, x0, x1, x2, x3);
+                    red_add_v4(cptr, x0, x1, x2, x3);
                 else
-                    *reinterpret_cast<float4*>(dst) = make_float4(x0, x1, x2, x3);
+                    *reinterpret_cast<float4*>(cptr) = make_float4(x0, x1, x2, x3);
             } else {
-                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.C) + static_cast<int64_t>(grow) * p.ldc + col) =
-                    make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+                *reinterpret_cast<uint2*>(cptr) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
             }
         }
+        cptr += rstride;
+        if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
+            if (pptr != nullptr) pptr += rstride;
+        }
     }
-    if (p.colsum != nullptr) {  // warp-uniform
-        // lanes l, l^8, l^16, l^24 hold the same 4 columns for different rows
-        cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
-        cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
-        cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
-        cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
-        if (lane < 8 && col_ok) red_add_v4(p.colsum + col, cs0, cs1, cs2, cs3);
+    if constexpr (EPI == B200CLIP_EPI_QUICKGELU_BWD) {
+        if (p.colsum != nullptr) {  // warp-uniform
+            // lanes l, l^8, l^16, l^24 hold the same 4 columns for different rows
+            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+            cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
+            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+            cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
+            if (lane < 8 && col_ok) red_add_v4(p.colsum + col, cs0, cs1, cs2, cs3);
+        }
     }
     __syncwarp();  // the staging tile is rewritten by the next block
 }
@@ -496,8 +512,9 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
     }
     B200_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias not 16B aligned");
     B200_CHECK_ARG(preact == nullptr || (reinterpret_cast<uintptr_t>(preact) & 15) == 0, "gemm: preact misaligned");
-    B200_CHECK_ARG(colsum == nullptr || ((reinterpret_cast<uintptr_t>(colsum) & 15) == 0 && split_k == 1 && !accumulate),
-                   "gemm: colsum needs a 16-byte aligned pointer and a non-split, non-accumulating GEMM");
+    B200_CHECK_ARG(colsum == nullptr || ((reinterpret_cast<uintptr_t>(colsum) & 15) == 0 &&
+                                         epilogue == B200CLIP_EPI_QUICKGELU_BWD && !out_f32),
+                   "gemm: colsum is fused into the EPI_QUICKGELU_BWD (bf16) epilogue only, 16-byte aligned");
 
     GemmParams p{};
     p.C = C;

@@ -83,8 +83,9 @@ int b200clip_ctx_destroy(b200clip_ctx* ctx);
  * except EPI_RESIDUAL with an fp32 C, where aux is fp32 too (the fp32 residual stream).
  * preact: bf16 [M,N] (ldc pitch) or NULL (EPI_QUICKGELU only).
  * scale: optional device fp32 scalar; acc is multiplied by it before bias (NULL = 1).
- * colsum: optional fp32 [N]; the column sums of C (after the epilogue) are ACCUMULATED into it -- the
- * bias gradient when C is a dgrad output (replaces a separate reduction pass over C).
+ * colsum: optional fp32 [N] (EPI_QUICKGELU_BWD only); the column sums of C (after the epilogue) are
+ * ACCUMULATED into it -- the c_fc bias gradient falls out of the c_proj dgrad instead of a separate
+ * reduction pass over C.
  * split_k > 1 splits the reduction over `split_k` CTAs per tile and ACCUMULATES into C with
  * fp32 atomics (requires out_dtype F32, EPI_NONE, no bias; C must be pre-zeroed or hold a
  * value to accumulate onto).  split_k = 0 lets the library choose (only when out is F32).
