@@ -146,7 +146,10 @@ class ParamStore:
             n = math.prod(shape)
             self.entries.append((name, p, off, shape))
             off += (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
-        self.total = off
+        # pad the flat length so that it splits evenly (in 64-element units) over 1..8 ranks: the
+        # trainer reduce-scatters gradients / all-gathers updated weights in equal shards
+        unit = self.ALIGN * 840
+        self.total = (off + unit - 1) // unit * unit
         self.w = torch.zeros(self.total, device=device, dtype=bf16)
         self.W = {name: self.w[o:o + math.prod(s)].view(s) for name, _, o, s in self.entries}
         self._seen = {}

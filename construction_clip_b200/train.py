@@ -120,7 +120,7 @@ class ClipTrainer:
     ``get_linear_schedule_with_warmup(5000, total)`` (CLIP/train.py:143-147)."""
 
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, warmup_steps=5000,
-                 total_steps=None, group=None, device=None):
+                 total_steps=None, group=None, device=None, shard_optimizer=True):
         self.model = model
         self.cfg = model.cfg
         self.group = group
@@ -130,13 +130,21 @@ class ClipTrainer:
         self.warmup_steps, self.total_steps = warmup_steps, total_steps
         self.step_count = 0
         self.stores = {k: model._store(k, self.device) for k in ("visual", "text")}
-        self.grads, self.master, self.m, self.v = {}, {}, {}, {}
+        # ZeRO-1 style optimiser sharding for N > 1: gradients are REDUCE-SCATTERED (each rank receives
+        # the sum of its 1/N slice), AdamW runs on that slice only (fp32 master / moments are 1/N the
+        # size) and the updated bf16 weights are all-gathered in place -- less NVLink traffic than an
+        # all-reduce (fp32 down, bf16 back) and 1/N of the optimiser's HBM traffic.
+        self.sharded = bool(shard_optimizer) and self.world > 1
+        self.grads, self.master, self.m, self.v, self.shard = {}, {}, {}, {}, {}
         for k, st in self.stores.items():
             st.sync()
             self.grads[k] = torch.zeros(st.total, device=self.device, dtype=f32)
-            self.master[k] = st.w.float()
-            self.m[k] = torch.zeros_like(self.grads[k])
-            self.v[k] = torch.zeros_like(self.grads[k])
+            n = st.total // self.world if self.sharded else st.total
+            lo = self.rank * n if self.sharded else 0
+            self.shard[k] = (lo, n)
+            self.master[k] = st.w[lo:lo + n].float()
+            self.m[k] = torch.zeros(n, device=self.device, dtype=f32)
+            self.v[k] = torch.zeros(n, device=self.device, dtype=f32)
         self.G = {k: self.stores[k].grad_views(self.grads[k]) for k in self.stores}
         self.ls_master = model.logit_scale.detach().to(f32).reshape(1).clone()
         self.ls_m = torch.zeros(1, device=self.device, dtype=f32)
@@ -144,6 +152,7 @@ class ClipTrainer:
         self.last_correct = None
         self.two_streams = True
         self._tower_streams = None
+        self._hyper_live = False  # True while a CUDA-graph capture / warm-up wants device-side lr
         # CUDA-graph mode (enable_cuda_graph): step-dependent scalars live in device memory
         self._use_graph = False
         self._graph = None
@@ -170,8 +179,11 @@ class ClipTrainer:
             return self.lr * max(0.0, (self.total_steps - s) / max(1, self.total_steps - self.warmup_steps))
         return self.lr
 
-    def forward_backward(self, image, text):
+    def forward_backward(self, image, text, fused_update=False):
         """Fills the flat gradient buffers with d(global loss)/d(params); returns the loss tensor.
+        ``fused_update`` (used by ``step``): with a sharded optimiser each tower's gradient
+        reduce-scatter, AdamW on the local shard and weight all-gather are issued on the tower's own
+        stream right after its backward; otherwise the gradients are sum-all-reduced in full.
 
         The two towers are independent until the loss, so they run on two CUDA streams: whenever a
         persistent GEMM of one tower leaves SMs idle in its last (partial) wave, CTAs of the other
@@ -208,14 +220,21 @@ class ClipTrainer:
             d_img.record_stream(sv)
             d_txt.record_stream(stt)
         work = []
+        hyper = self._hyper if self._hyper_live else None
         with torch.cuda.stream(sv):
             T.vision_bwd(Wv, self.G["visual"], cfg, saved_i, d_img)
             if self.world > 1:
-                work.append(dist.all_reduce(self.grads["visual"], group=self.group, async_op=True))
+                if fused_update and self.sharded:
+                    self._sharded_update("visual", hyper)
+                else:
+                    work.append(dist.all_reduce(self.grads["visual"], group=self.group, async_op=True))
         with torch.cuda.stream(stt):
             T.text_bwd(Wt, self.G["text"], cfg, saved_t, d_txt)
             if self.world > 1:
-                work.append(dist.all_reduce(self.grads["text"], group=self.group, async_op=True))
+                if fused_update and self.sharded:
+                    self._sharded_update("text", hyper)
+                else:
+                    work.append(dist.all_reduce(self.grads["text"], group=self.group, async_op=True))
         if two:
             main.wait_stream(sv)
             main.wait_stream(stt)
@@ -227,19 +246,34 @@ class ClipTrainer:
         self.last_correct = st.correct
         return st.loss
 
-    def optimizer_step(self, hyper=None):
-        """AdamW on both flat buffers + logit_scale.  ``hyper`` (device float[3]) carries lr and the
-        bias corrections when the step is replayed from a CUDA graph."""
-        if hyper is None:
-            self.step_count += 1
-        lr = self.current_lr() if hyper is None else 0.0
-        step = self.step_count if hyper is None else 0
+    def _adam_args(self, hyper):
         b1, b2 = self.betas
-        for k, st in self.stores.items():
-            O.adamw(self.master[k], st.w, self.grads[k], self.m[k], self.v[k], lr=lr, beta1=b1, beta2=b2, eps=self.eps,
-                    weight_decay=self.wd, grad_scale=1.0, step=step, hyper=hyper)
-        O.adamw(self.ls_master, None, self.d_ls, self.ls_m, self.ls_v, lr=lr, beta1=b1, beta2=b2, eps=self.eps,
-                weight_decay=self.wd, grad_scale=1.0, step=step, hyper=hyper)
+        return dict(lr=self.current_lr() if hyper is None else 0.0, beta1=b1, beta2=b2, eps=self.eps,
+                    weight_decay=self.wd, grad_scale=1.0, step=self.step_count if hyper is None else 0, hyper=hyper)
+
+    def _sharded_update(self, k, hyper):
+        """reduce-scatter(grad) -> AdamW on the local shard -> all-gather(bf16 weights), on the current stream."""
+        st = self.stores[k]
+        lo, n = self.shard[k]
+        gshard = self.grads[k][lo:lo + n]
+        dist.reduce_scatter_tensor(gshard, self.grads[k], group=self.group)
+        O.adamw(self.master[k], st.w[lo:lo + n], gshard, self.m[k], self.v[k], **self._adam_args(hyper))
+        dist.all_gather_into_tensor(st.w, st.w[lo:lo + n], group=self.group)
+
+    def optimizer_step(self, hyper=None, towers=True, _count=True):
+        """AdamW on both flat buffers + logit_scale.  ``hyper`` (device float[3]) carries lr and the
+        bias corrections when the step is replayed from a CUDA graph.  With a sharded optimiser the
+        gradients in ``self.grads`` must NOT have been all-reduced yet (``step`` fuses the tower
+        updates into ``forward_backward``; this entry point then only handles logit_scale)."""
+        if _count and hyper is None:
+            self.step_count += 1
+        if towers:
+            for k, st in self.stores.items():
+                if self.sharded:
+                    self._sharded_update(k, hyper)
+                else:
+                    O.adamw(self.master[k], st.w, self.grads[k], self.m[k], self.v[k], **self._adam_args(hyper))
+        O.adamw(self.ls_master, None, self.d_ls, self.ls_m, self.ls_v, **self._adam_args(hyper))
         with torch.no_grad():
             self.model.logit_scale.copy_(self.ls_master.reshape(()))
 
@@ -272,8 +306,10 @@ class ClipTrainer:
             for _ in range(2):
                 self.step_count += 1
                 self._push_hyper()
-                self.forward_backward(self._g_img, self._g_txt)
-                self.optimizer_step(hyper=self._hyper)
+                self._hyper_live = True
+                self.forward_backward(self._g_img, self._g_txt, fused_update=True)
+                self.optimizer_step(hyper=self._hyper, towers=not self.sharded, _count=False)
+                self._hyper_live = False
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         with torch.no_grad():
@@ -284,8 +320,10 @@ class ClipTrainer:
         del backup
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            loss = self.forward_backward(self._g_img, self._g_txt)
-            self.optimizer_step(hyper=self._hyper)
+            self._hyper_live = True
+            loss = self.forward_backward(self._g_img, self._g_txt, fused_update=True)
+            self.optimizer_step(hyper=self._hyper, towers=not self.sharded, _count=False)
+            self._hyper_live = False
             self._g_loss = loss.reshape(1).clone()
             self._g_correct = self.last_correct.reshape(1).clone()
         self._graph = graph
@@ -308,10 +346,14 @@ class ClipTrainer:
         (e.g. after ``model.float()``); linked bf16 parameters are already up to date."""
         with torch.no_grad():
             for k, st in self.stores.items():
+                full = self.master[k]
+                if self.sharded:
+                    full = torch.empty(st.total, device=self.device, dtype=f32)
+                    dist.all_gather_into_tensor(full, self.master[k], group=self.group)
                 for name, p, o, s in st.entries:
                     if p.data_ptr() != st.W[name].data_ptr():
                         n = math.prod(s)
-                        src = self.master[k][o:o + n].view(s)
+                        src = full[o:o + n].view(s)
                         if tuple(s) != tuple(p.shape):
                             src = src[:, :math.prod(p.shape[1:])]
                         p.copy_(src.reshape(p.shape))
@@ -357,6 +399,7 @@ class ClipTrainer:
         global batch; returns the global mean loss as a device tensor (no host sync)."""
         if self._use_graph:
             return self._graph_step(image, text)
-        loss = self.forward_backward(image, text)
-        self.optimizer_step()
+        self.step_count += 1
+        loss = self.forward_backward(image, text, fused_update=True)
+        self.optimizer_step(towers=not self.sharded, _count=False)
         return loss

@@ -32,7 +32,7 @@ def main():
 
     # sharded trainer step (flat fp32 grads, all-reduced)
     m = device_model(name, orc, device=dev).train()
-    tr = ClipTrainer(m, lr=1e-4, warmup_steps=0)
+    tr = ClipTrainer(m, lr=1e-4, warmup_steps=0, shard_optimizer=False)
     loss = tr.forward_backward(img[sl].to(dev), tok[sl].to(dev))
     torch.cuda.synchronize()
     flat_sharded = {k: v.clone() for k, v in tr.grads.items()}
@@ -83,6 +83,21 @@ def main():
     same = torch.equal(w, w0)
     if not same:
         ok = False
+    # sharded optimiser (reduce-scatter + AdamW on 1/N + all-gather) == replicated AdamW on all-reduced grads
+    wsh = []
+    for shard in (False, True):
+        ms = device_model(name, orc, device=dev).train()
+        ts = ClipTrainer(ms, lr=1e-3, warmup_steps=0, shard_optimizer=shard)
+        for _ in range(2):
+            ts.step(img[sl].to(dev), tok[sl].to(dev).int())
+        torch.cuda.synchronize()
+        wsh.append((ts.stores["visual"].w.float().clone(), ts.stores["text"].w.float().clone()))
+        del ts, ms
+    shard_diff = max((wsh[0][0] - wsh[1][0]).abs().max().item(), (wsh[0][1] - wsh[1][1]).abs().max().item())
+    wcheck = wsh[1][0].clone()
+    dist.broadcast(wcheck, 0)
+    if shard_diff > 2e-2 or not torch.equal(wcheck, wsh[1][0]):
+        ok = False
     # CUDA-graph replay of the whole sharded step (NCCL collectives captured) == eager
     ga = gb = 0.0
     if os.environ.get("DIST_GRAPH", "1") == "1":
@@ -104,7 +119,7 @@ def main():
     if rank == 0:
         print(f"DIST_CHECK world={world} Bg={Bg} loss_sharded={loss.item():.6f} loss_single={loss1.item():.6f} rel={rel:.2e} "
               f"worst_grad_cos={worst:.6f} dls_rel={dls:.2e} autograd_cos={c2:.6f} replicas_identical={same} "
-              f"graph_vs_eager_loss={gb:.5f}/{ga:.5f} "
+              f"graph_vs_eager_loss={gb:.5f}/{ga:.5f} sharded_vs_replicated_maxdiff={shard_diff:.2e} "
               f"RESULT={'PASS' if flag.item() == 1.0 else 'FAIL'}", flush=True)
     code = 0 if flag.item() == 1.0 else 1
     import gc
