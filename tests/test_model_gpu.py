@@ -254,8 +254,8 @@ def test_cuda_graph_step_matches_eager():
                      m.logit_scale.item(), tr.step_count))
     (l0, wv0, wt0, ls0, c0), (l1, wv1, wt1, ls1, c1) = runs
     assert c0 == c1 == 6
-    for a, b in zip(l0, l1):
-        assert abs(a - b) <= 2e-3 * max(1.0, abs(a)), (l0, l1)
+    for i, (a, b) in enumerate(zip(l0, l1)):
+        assert abs(a - b) <= (1e-4 if i == 0 else 1e-2) * max(1.0, abs(a)), (l0, l1)
     # split-K fp32 atomics reorder sums between runs: weights agree to bf16 resolution, not bitwise
     assert (wv0 - wv1).abs().max().item() <= 2e-2 and (wt0 - wt1).abs().max().item() <= 2e-2
     assert abs(ls0 - ls1) < 1e-4

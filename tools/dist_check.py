@@ -98,6 +98,8 @@ def main():
     dist.broadcast(wcheck, 0)
     if shard_diff > 2e-2 or not torch.equal(wcheck, wsh[1][0]):
         ok = False
+        print(f"rank {rank}: sharded optimiser mismatch: maxdiff {shard_diff}, replicas equal "
+              f"{torch.equal(wcheck, wsh[1][0])}", flush=True)
     # CUDA-graph replay of the whole sharded step (NCCL collectives captured) == eager
     ga = gb = 0.0
     if os.environ.get("DIST_GRAPH", "1") == "1":
@@ -111,9 +113,12 @@ def main():
             tg.enable_cuda_graph(False)  # drop the captured graph before the communicator is torn down
             del tg, mg
         ga, gb = res[0][-1], res[1][-1]
-        for a, b in zip(*res):
-            if abs(a - b) > 2e-3 * max(1.0, abs(a)):
+        # identical weights at step 0 -> same loss up to summation order; afterwards Adam's sign-like
+        # first updates amplify the (split-K atomics) reduction-order noise, so later steps get 1e-2
+        for i, (a, b) in enumerate(zip(*res)):
+            if abs(a - b) > (1e-4 if i == 0 else 1e-2) * max(1.0, abs(a)):
                 ok = False
+                print(f"rank {rank}: graph/eager loss mismatch at step {i}: {a} vs {b}", flush=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
