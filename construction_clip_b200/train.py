@@ -332,7 +332,13 @@ class ClipTrainer:
     def _graph_step(self, image, text):
         key = (tuple(image.shape), image.dtype, tuple(text.shape), text.dtype)
         if self._graph is None or self._graph_key != key:
-            self._capture(image, text)
+            try:
+                self._capture(image, text)
+            except Exception as e:  # capture is an optimisation: fall back to eager launches
+                import warnings
+                warnings.warn(f"CUDA-graph capture of the training step failed ({e!r}); running eagerly")
+                self._use_graph, self._graph, self._hyper_live = False, None, False
+                return self.step(image, text)
         self._g_img.copy_(image, non_blocking=True)
         self._g_txt.copy_(text, non_blocking=True)
         self.step_count += 1
