@@ -248,6 +248,12 @@ def run_ours(args):
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in gemm_prof)
     gemm_flops = sum(f for _, _, f, _ in gemm_prof)
     gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    gemm_alg_bytes = sum(info[5] for _, _, _, info in gemm_prof) / max(1, len(gemm_prof))
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    if world == 1 and os.path.exists(tpath):   # ncu capture of the same workload (N = 1), committed under profiles/
+        with open(tpath) as fh:
+            traffic = json.load(fh).get("dram_bytes_per_launch")
 
     # ---------------- end to end through the host-facing API (`e2e`) ----------------
     for i in range(max(2, args.warmup)):
@@ -312,7 +318,9 @@ def run_ours(args):
         "clocks": clocks,
         "roofline": {
             "bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
-            "frac": gemm_tflops / peaks["bf16_sustained"], "traffic": None,
+            "frac": gemm_tflops / peaks["bf16_sustained"], "traffic": traffic,
+            "traffic_unit": "DRAM bytes per GEMM launch (ncu, profiles/r01_gemm_traffic.json)",
+            "algorithmic_bytes_per_launch_avg": gemm_alg_bytes,
             "kernel": "gemm_bf16_kernel (tcgen05, all fwd/dgrad/wgrad launches)",
             "peak_source": f"{peaks['source']} (sustained cuBLAS bf16; kernel timed inside a long step)",
             "launches_timed": len(gemm_prof),

@@ -77,7 +77,10 @@ def gemm(a, b, *, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, aux=None, pre
         split_k, 1 if accumulate else 0, st), "gemm_bf16")
     if prof is not None:
         e1.record()
-        prof.append((e0, e1, 2.0 * M * N * K, (a_major, b_major, M, N, K)))
+        nbytes = (a.numel() + b.numel()) * 2 + out.numel() * out.element_size()
+        nbytes += aux.numel() * aux.element_size() if aux is not None else 0
+        nbytes += preact.numel() * 2 if preact is not None else 0
+        prof.append((e0, e1, 2.0 * M * N * K, (a_major, b_major, M, N, K, nbytes)))
     return out
 
 
