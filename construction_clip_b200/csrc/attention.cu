@@ -545,6 +545,251 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Backward for sequences longer than one tile (ViT-B/16 / ViT-L/14 fine-tuning): two passes over the
+// 128 x 128 blocks of the score matrix, both recomputing S = Q K^T and dP = dO V^T on the tensor core.
+//   MODE 0: one CTA per (sample, head, KV block j), loops over the query blocks i and accumulates
+//           dV_j += P_ij^T dO_i, dK_j += dS_ij^T Q_i in TMEM;
+//   MODE 1: one CTA per (sample, head, query block i), loops over the KV blocks j and accumulates
+//           dQ_i += dS_ij K_j in TMEM.
+// P = exp2(S * sc - lse) needs the forward's row log-sum-exp, dS = P o (dP - D) / 8 the row sums
+// D = rowsum(dO o O), precomputed by attn_delta_kernel.  Two threads per score row, 256 threads.
+__global__ void __launch_bounds__(256)
+attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout, float* __restrict__ delta,
+                  int B, int S, int H) {
+    // delta[(b*H + h)*S + s] = sum_c dO[b*S+s, h*64+c] * O[b*S+s, h*64+c]; one thread per (token, head)
+    const int64_t n = static_cast<int64_t>(B) * S * H;
+    const int d = H * 64;
+    for (int64_t t = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; t < n;
+         t += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int h = static_cast<int>(t % H);
+        const int64_t tok = t / H;
+        const uint4* po = reinterpret_cast<const uint4*>(o + tok * d + h * 64);
+        const uint4* pd = reinterpret_cast<const uint4*>(dout + tok * d + h * 64);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            const uint4 a = __ldg(po + c), g = __ldg(pd + c);
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, gw[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 x = unpack_bf16(aw[j]), y = unpack_bf16(gw[j]);
+                acc = fmaf(x.x, y.x, acc);
+                acc = fmaf(x.y, y.y, acc);
+            }
+        }
+        const int64_t b = tok / S, srow = tok % S;
+        delta[(b * H + h) * S + srow] = acc;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kAttnBwdThreads)
+attn_bwd_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                     const AttnParams p, const float* __restrict__ delta) {
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t bar_outer, bar_inner, bar_mma;
+    __shared__ uint32_t tmem_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sP = smem;               // 2 tiles
+    uint8_t* sdS = sP + 2 * kTile;    // 2 tiles
+    uint8_t* sQ = sdS + 2 * kTile;
+    uint8_t* sdO = sQ + kTile;
+    uint8_t* sK = sdO + kTile;
+    uint8_t* sV = sK + kTile;
+    constexpr int kTmemCols = 512;    // [0,128) S, [128,256) dP, [256,320) dV | dQ, [320,384) dK
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = (warp & 3) * 32 + lane;
+    const int half = warp >> 2;
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tm_qkv);
+        prefetch_tmap(&tm_do);
+        mbar_init(&bar_outer, 1);
+        mbar_init(&bar_inner, 1);
+        mbar_init(&bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc(&tmem_slot, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+
+    const int S = p.S, H = p.H;
+    const int d = H * 64;
+    const int nblk = (S + 127) / 128;
+    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t idesc_tn = make_idesc_bf16(128, 64, 1, 1);
+    const uint32_t idesc_nn = make_idesc_bf16(128, 64, 0, 1);
+    const float sc = 0.125f * kLog2e;
+    const int num_work = p.B * H * nblk;
+    uint32_t it = 0, in_it = 0;
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
+        const int ob = w % nblk;  // outer block: KV block (MODE 0) / query block (MODE 1)
+        const int bh = w / nblk;
+        const int b = bh / H, h = bh % H;
+        const int o0 = ob * 128;
+        const int64_t tok0 = static_cast<int64_t>(b) * S;
+        if (threadIdx.x == 0) {
+            mbar_arrive_expect_tx(&bar_outer, 2 * kTile);
+            if (MODE == 0) {
+                tma_load_2d(sK, &tm_qkv, &bar_outer, d + h * 64, static_cast<int>(tok0) + o0);
+                tma_load_2d(sV, &tm_qkv, &bar_outer, 2 * d + h * 64, static_cast<int>(tok0) + o0);
+            } else {
+                tma_load_2d(sQ, &tm_qkv, &bar_outer, h * 64, static_cast<int>(tok0) + o0);
+                tma_load_2d(sdO, &tm_do, &bar_outer, h * 64, static_cast<int>(tok0) + o0);
+            }
+        }
+        // inner range (causal: only blocks that intersect the lower triangle)
+        const int ib0 = (MODE == 0) ? (p.causal ? ob : 0) : 0;
+        const int ib1 = (MODE == 0) ? nblk : (p.causal ? ob + 1 : nblk);
+        bool first = true;
+        for (int ib = ib0; ib < ib1; ++ib, ++in_it) {
+            const int i0 = ib * 128;
+            const int q0 = (MODE == 0) ? i0 : o0;   // query block start
+            const int k0 = (MODE == 0) ? o0 : i0;   // kv block start
+            if (threadIdx.x == 0) {
+                mbar_arrive_expect_tx(&bar_inner, 2 * kTile);
+                if (MODE == 0) {
+                    tma_load_2d(sQ, &tm_qkv, &bar_inner, h * 64, static_cast<int>(tok0) + i0);
+                    tma_load_2d(sdO, &tm_do, &bar_inner, h * 64, static_cast<int>(tok0) + i0);
+                } else {
+                    tma_load_2d(sK, &tm_qkv, &bar_inner, d + h * 64, static_cast<int>(tok0) + i0);
+                    tma_load_2d(sV, &tm_qkv, &bar_inner, 2 * d + h * 64, static_cast<int>(tok0) + i0);
+                }
+            }
+            const int qrow = q0 + r;
+            const bool live = qrow < S;
+            float m2 = 0.f, D = 0.f;
+            if (live) {
+                const int64_t si = (static_cast<int64_t>(b) * H + h) * S + qrow;
+                m2 = p.lse[si];
+                D = delta[si];
+            }
+            if (threadIdx.x == 0) {
+                if (first) mbar_wait(&bar_outer, it & 1u);
+                mbar_wait(&bar_inner, in_it & 1u);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem, make_smem_desc_sw128(smem_u32(sQ) + k * 32, 16, 1024),
+                              make_smem_desc_sw128(smem_u32(sK) + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem + 128, make_smem_desc_sw128(smem_u32(sdO) + k * 32, 16, 1024),
+                              make_smem_desc_sw128(smem_u32(sV) + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, 0u);
+            __syncwarp();
+            tc_fence_after();
+            for (int ci = half * 4; ci < half * 4 + 4; ++ci) {
+                const int c0 = ci << 4;
+                uint32_t v[16], g[16];
+                tmem_ld_32x16(trow + c0, v);
+                tmem_ld_32x16(trow + 128 + c0, g);
+                tmem_ld_wait();
+                float pe[16], ds[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const int col = k0 + c0 + j;
+                    const bool msk = !live || col >= S || (p.causal && col > qrow);
+                    const float e = msk ? 0.f : exp2f(__uint_as_float(v[j]) * sc - m2);
+                    pe[j] = e;
+                    ds[j] = msk ? 0.f : e * (__uint_as_float(g[j]) - D) * 0.125f;
+                }
+                *reinterpret_cast<uint4*>(p_chunk(sP, kTile, r, c0 >> 3)) =
+                    make_uint4(pack_bf16(pe[0], pe[1]), pack_bf16(pe[2], pe[3]), pack_bf16(pe[4], pe[5]), pack_bf16(pe[6], pe[7]));
+                *reinterpret_cast<uint4*>(p_chunk(sP, kTile, r, (c0 >> 3) + 1)) =
+                    make_uint4(pack_bf16(pe[8], pe[9]), pack_bf16(pe[10], pe[11]), pack_bf16(pe[12], pe[13]), pack_bf16(pe[14], pe[15]));
+                *reinterpret_cast<uint4*>(p_chunk(sdS, kTile, r, c0 >> 3)) =
+                    make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+                *reinterpret_cast<uint4*>(p_chunk(sdS, kTile, r, (c0 >> 3) + 1)) =
+                    make_uint4(pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]), pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                tc_fence_after();
+                const uint32_t acc = first ? 0u : 1u;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (MODE == 0) {
+                        const uint64_t a_pt = make_smem_desc_sw128(smem_u32(sP) + k * 2048, kTile, 1024);
+                        const uint64_t a_dst = make_smem_desc_sw128(smem_u32(sdS) + k * 2048, kTile, 1024);
+                        const uint64_t b_do = make_smem_desc_sw128(smem_u32(sdO) + k * 2048, 8192, 1024);
+                        const uint64_t b_q = make_smem_desc_sw128(smem_u32(sQ) + k * 2048, 8192, 1024);
+                        umma_bf16(tmem + 256, a_pt, b_do, idesc_tn, (k > 0) ? 1u : acc);   // dV_j += P^T dO_i
+                        umma_bf16(tmem + 320, a_dst, b_q, idesc_tn, (k > 0) ? 1u : acc);   // dK_j += dS^T Q_i
+                    } else {
+                        const uint64_t a_ds = make_smem_desc_sw128(smem_u32(sdS) + (k >> 2) * kTile + (k & 3) * 32, 16, 1024);
+                        const uint64_t b_k = make_smem_desc_sw128(smem_u32(sK) + k * 2048, 8192, 1024);
+                        umma_bf16(tmem + 256, a_ds, b_k, idesc_nn, (k > 0) ? 1u : acc);    // dQ_i += dS K_j
+                    }
+                }
+                umma_commit(&bar_mma);
+            }
+            mbar_wait(&bar_mma, 1u);   // the inner tiles, P and dS are rewritten by the next iteration
+            __syncwarp();
+            tc_fence_after();
+            tc_fence_before();
+            __syncthreads();
+            tc_fence_after();
+            first = false;
+        }
+        // ---- outputs of this work item
+        {
+            const int orow = o0 + r;
+            const bool ok = orow < S && !first;
+            __nv_bfloat16* dst = p.out + (tok0 + orow) * (3 * d) + h * 64;
+            if (MODE == 0) {
+                // half 0 stores dV (TMEM 256..319) into the v slot, half 1 stores dK (320..383) into the k slot
+                const uint32_t tcol = half == 0 ? 256u : 320u;
+                __nv_bfloat16* dd = dst + (half == 0 ? 2 * d : d);
+#pragma unroll
+                for (int c0 = 0; c0 < 64; c0 += 32) {
+                    uint32_t v[32];
+                    tmem_ld_32x32(trow + tcol + c0, v);
+                    tmem_ld_wait();
+                    if (ok) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8)
+                            *reinterpret_cast<uint4*>(dd + c0 + j) =
+                                make_uint4(pack_bf16(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                                           pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])),
+                                           pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])),
+                                           pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+                    }
+                }
+            } else {
+                const int c0 = half * 32;
+                uint32_t v[32];
+                tmem_ld_32x32(trow + 256 + c0, v);
+                tmem_ld_wait();
+                if (ok) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8)
+                        *reinterpret_cast<uint4*>(dst + c0 + j) =
+                            make_uint4(pack_bf16(__uint_as_float(v[j]), __uint_as_float(v[j + 1])),
+                                       pack_bf16(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])),
+                                       pack_bf16(__uint_as_float(v[j + 4]), __uint_as_float(v[j + 5])),
+                                       pack_bf16(__uint_as_float(v[j + 6]), __uint_as_float(v[j + 7])));
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
+    if (warp == 0) {
+        __syncwarp();
+        tmem_dealloc(tmem, kTmemCols);
+    }
+}
+
 // dynamic shared memory: compact tiles (A operands first, so their 128-row reads stay inside) + alignment.
 // The last A tile (Q fwd / dO bwd) is followed by >= 2 more tiles of npad >= 16 rows... not enough when
 // npad < 43: keep the allocation at least kTile past the start of that tile.
@@ -568,6 +813,10 @@ int init_attention(b200clip_ctx*) {
         e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(true, 128));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(attn_fwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * kTile + 1024);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_bwd_long_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kTile + 1024);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_bwd_long_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kTile + 1024);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem(false, 64));
     if (e == cudaSuccess)
@@ -653,11 +902,42 @@ extern "C" int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, 
 }
 
 extern "C" int b200clip_attn_bwd(b200clip_ctx* ctx, const void* qkv, const void* out, const float* lse,
-                                 const void* dout, void* dqkv, int64_t B, int64_t S, int64_t H, int causal,
-                                 void* stream) {
-    int rc = check_attn_args(ctx, qkv, dout, B, S, H, false);
+                                 const void* dout, void* dqkv, void* workspace, int64_t workspace_bytes, int64_t B,
+                                 int64_t S, int64_t H, int causal, void* stream) {
+    int rc = check_attn_args(ctx, qkv, dout, B, S, H, true);
     if (rc) return rc;
     B200_CHECK_ARG(out && lse, "attention bwd: needs the forward's out and lse");
+    if (S > 128) {
+        B200_CHECK_ARG(workspace != nullptr && workspace_bytes >= static_cast<int64_t>(B * H * S * sizeof(float)),
+                       "attention bwd (S > 128): needs a workspace of B*H*S floats");
+        B200_CHECK_ARG(dqkv && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0, "attention: dqkv null / misaligned");
+        CUtensorMap tmq, tmd;
+        if ((rc = make_tmap_bf16_2d(ctx, &tmq, qkv, 3 * H * 64, B * S, 3 * H * 64, 64, 128))) return rc;
+        if ((rc = make_tmap_bf16_2d(ctx, &tmd, dout, H * 64, B * S, H * 64, 64, 128))) return rc;
+        AttnParams pl{};
+        pl.o = static_cast<const __nv_bfloat16*>(out);
+        pl.lse = const_cast<float*>(lse);
+        pl.out = static_cast<__nv_bfloat16*>(dqkv);
+        pl.B = static_cast<int>(B);
+        pl.S = static_cast<int>(S);
+        pl.H = static_cast<int>(H);
+        pl.causal = causal ? 1 : 0;
+        pl.npad = 128;
+        float* delta = static_cast<float*>(workspace);
+        cudaStream_t stl = static_cast<cudaStream_t>(stream);
+        const int64_t nd = B * S * H;
+        const int gd = static_cast<int>(ceil_div(nd, 256) < ctx->num_sms * 8 ? ceil_div(nd, 256) : ctx->num_sms * 8);
+        attn_delta_kernel<<<gd, 256, 0, stl>>>(pl.o, static_cast<const __nv_bfloat16*>(dout), delta, pl.B, pl.S, pl.H);
+        B200_LAUNCH_CHECK();
+        const int64_t work_l = B * H * ((S + 127) / 128);
+        B200_CHECK_ARG(work_l < (1ll << 31), "attention: extent too large");
+        const int grid_l = static_cast<int>(work_l < ctx->num_sms ? work_l : ctx->num_sms);
+        attn_bwd_long_kernel<0><<<grid_l, kAttnBwdThreads, 8 * kTile + 1024, stl>>>(tmq, tmd, pl, delta);
+        B200_LAUNCH_CHECK();
+        attn_bwd_long_kernel<1><<<grid_l, kAttnBwdThreads, 8 * kTile + 1024, stl>>>(tmq, tmd, pl, delta);
+        B200_LAUNCH_CHECK();
+        return 0;
+    }
     B200_CHECK_ARG(dqkv && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                    "attention: dqkv / out null or misaligned");
     CUtensorMap tm, tmdo;

@@ -151,9 +151,11 @@ def attn_bwd(qkv, out, lse, dout, B, S, H, causal, dqkv=None):
     assert qkv.is_contiguous() and dout.is_contiguous() and out.is_contiguous() and dout.shape == (B * S, H * 64)
     if dqkv is None:
         dqkv = torch.empty_like(qkv)
+    ws = torch.empty(B * H * S, device=qkv.device, dtype=f32) if S > 128 else None
     ctx, st = _ctx_stream(qkv)
     L.check(L.load().b200clip_attn_bwd(ctx, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), dout.data_ptr(),
-                                       dqkv.data_ptr(), B, S, H, 1 if causal else 0, st), "attn_bwd")
+                                       dqkv.data_ptr(), _ptr(ws), ws.numel() * 4 if ws is not None else 0, B, S, H,
+                                       1 if causal else 0, st), "attn_bwd")
     return dqkv
 
 

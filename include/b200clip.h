@@ -122,16 +122,17 @@ int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t lddy, cons
 /* ---- nn.MultiheadAttention(need_weights=False) core: softmax(q k^T / 8 + mask) v, head_dim 64 ----
  * qkv: bf16 [B*S, 3*H*64] (the packed in_proj output: q | k | v, each head-major), out: bf16 [B*S, H*64].
  * causal != 0 applies upstream's build_attention_mask (-inf strictly above the diagonal; padding is
- * NOT masked).  S <= 128 runs the single-tile kernel; longer sequences (ViT-B/16, ViT-L/14) stream the
- * keys/values in 128-row blocks (forward only: b200clip_attn_bwd returns B200CLIP_ERR_UNSUPPORTED for
- * S > 128 in this version). */
+ * NOT masked).  S <= 128 runs the single-tile kernels; longer sequences (ViT-B/16: 197, ViT-L/14: 257,
+ * ViT-L/14@336px: 577 tokens) stream the keys/values in 128-row blocks. */
 int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, float* lse, int64_t B, int64_t S, int64_t H,
                       int causal, void* stream);
 /* dqkv: bf16 [B*S, 3*H*64].  `out` and `lse` are the forward's results (lse: fp32 [B*H*S], the row
  * log-sum-exp in the log2 domain; pass a buffer to b200clip_attn_fwd when a backward will follow,
- * NULL otherwise); probabilities are recomputed from q,k and lse. */
+ * NULL otherwise); probabilities are recomputed from q,k and lse.  workspace: device scratch of at least
+ * B*H*S floats, required when S > 128 (rowsum(dO o O) for the two-pass blocked backward), else may be NULL. */
 int b200clip_attn_bwd(b200clip_ctx* ctx, const void* qkv, const void* out, const float* lse, const void* dout,
-                      void* dqkv, int64_t B, int64_t S, int64_t H, int causal, void* stream);
+                      void* dqkv, void* workspace, int64_t workspace_bytes, int64_t B, int64_t S, int64_t H, int causal,
+                      void* stream);
 
 /* ---- token_embedding(text) + positional_embedding  (clip.model.CLIP.encode_text) ---------------
  * ids int32 [B,S]; table bf16 [V,d]; pos bf16 [S,d]; out bf16 or f32 (out_dtype) [B*S,d]; eot_row int32 [B] receives

@@ -191,6 +191,12 @@ def test_attention_fwd_long(ops, B, S, H, causal):
     if causal:
         sc = sc + torch.full((S, S), float("-inf"), device="cuda").triu_(1)
     _close(lse.view(B, H, S), torch.logsumexp(sc, -1) * 1.4426950408889634, 2e-3, 1e-3, "lse (log2)")
+    # blocked two-pass backward (dK/dV pass + dQ pass)
+    qr = qkv.float().requires_grad_(True)
+    dout = _rand((B * S, H * 64), seed=S + 1)
+    _attn_ref(qr, B, S, H, causal).backward(dout.float())
+    dqkv = ops.attn_bwd(qkv, out, lse, dout, B, S, H, causal)
+    _close(dqkv, qr.grad, 4e-2, 4e-2, "attn bwd long")
 
 
 def test_embed_tokens(ops):

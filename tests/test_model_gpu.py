@@ -295,3 +295,23 @@ def test_forward_vitl14_padded_patch_embed():
     assert fi.shape == (2, 768)
     assert cosine_rows(fi.float().cpu(), fi_ref).min() >= 0.999
     assert (lpi.float().cpu() - lpi_ref).abs().max().item() <= LOGIT_TOL
+
+
+def test_train_step_vitb16_long_sequence_backward():
+    """Fine-tune step of ViT-B/16 (197 vision tokens): exercises the blocked two-pass attention
+    backward.  Loss within 1e-3, every gradient tensor cosine >= 0.99 against oracle autograd."""
+    from oracle import clip_oracle as O
+    name, B = "ViT-B/16", 4
+    orc = oracle_model(name)
+    img, tok = _inputs(name, B, B, 12)
+    lpi_ref, lpt_ref = orc(img, tok)
+    loss_ref = O.clip_loss(lpi_ref, lpt_ref)
+    loss_ref.backward()
+    ref_grads = {n: p.grad for n, p in orc.named_parameters()}
+    m = device_model(name, orc).train()
+    lpi, lpt = m(img.cuda(), tok.cuda())
+    label = torch.arange(B, device="cuda")
+    loss = (torch.nn.functional.cross_entropy(lpi, label) + torch.nn.functional.cross_entropy(lpt, label)) / 2
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-3 * abs(loss_ref.item())
+    _compare_grads({n: p.grad for n, p in m.named_parameters()}, ref_grads)
