@@ -315,3 +315,25 @@ def test_train_step_vitb16_long_sequence_backward():
     loss.backward()
     assert abs(loss.item() - loss_ref.item()) <= 1e-3 * abs(loss_ref.item())
     _compare_grads({n: p.grad for n, p in m.named_parameters()}, ref_grads)
+
+
+def test_train_step_vitl14_padded_conv_backward():
+    """ViT-L/14 fine-tune step on 2 pairs: width-1024 LayerNorm kernels, 257-token blocked attention
+    backward, and the wgrad of the zero-padded (588 -> 640) patch-embedding weight, whose gradient is
+    sliced back to upstream's [1024, 3, 14, 14] shape."""
+    from oracle import clip_oracle as O
+    name, B = "ViT-L/14", 2
+    orc = oracle_model(name)
+    img, tok = _inputs(name, B, B, 12)
+    lpi_ref, lpt_ref = orc(img, tok)
+    loss_ref = O.clip_loss(lpi_ref, lpt_ref)
+    loss_ref.backward()
+    ref_grads = {n: p.grad for n, p in orc.named_parameters()}
+    m = device_model(name, orc).train()
+    lpi, lpt = m(img.cuda(), tok.cuda())
+    label = torch.arange(B, device="cuda")
+    loss = (torch.nn.functional.cross_entropy(lpi, label) + torch.nn.functional.cross_entropy(lpt, label)) / 2
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) <= 1e-3 * abs(loss_ref.item())
+    assert m.visual.conv1.weight.grad.shape == (1024, 3, 14, 14)
+    _compare_grads({n: p.grad for n, p in m.named_parameters()}, ref_grads)
