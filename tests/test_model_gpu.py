@@ -337,3 +337,34 @@ def test_train_step_vitl14_padded_conv_backward():
     assert abs(loss.item() - loss_ref.item()) <= 1e-3 * abs(loss_ref.item())
     assert m.visual.conv1.weight.grad.shape == (1024, 3, 14, 14)
     _compare_grads({n: p.grad for n, p in m.named_parameters()}, ref_grads)
+
+
+def test_batched_prefix_extraction_matches_per_image_loop(tmp_path):
+    """construction_clip_b200.extract: same pickle contents as the per-image loop of
+    CLIP_prefix_caption/parse_coco.py:37-65 replayed through the drop-in model."""
+    import pickle
+    from construction_clip_b200.extract import extract_prefix_features
+    name = "ViT-B/32"
+    orc = oracle_model(name)
+    m = device_model(name, orc).eval()
+    n = 7
+    img, tok = _inputs(name, n, 11, 12)
+    cap_tok, vio_tok = tok[:2], tok[2:]
+    ann = [{"id": i, "caption": f"c{i}", "file_name": f"{i}.jpg"} for i in range(n)]
+    out = extract_prefix_features(m, (img[i] for i in range(n)), ann, cap_tok, vio_tok, batch_size=3,
+                                  out_path=str(tmp_path / "emb.pkl"))
+    with open(tmp_path / "emb.pkl", "rb") as fh:
+        loaded = pickle.load(fh)
+    assert loaded["clip_embedding"].shape == (n, 512) and len(loaded["captions"]) == n
+    cap_labels, vio_labels = ["現況", "缺失"], ["墜落", "防護具", "感電", "工作場所", "物料", "爆炸", "穿刺", "機械", "搬運"]
+    with torch.no_grad():
+        for i in range(n):                       # the reference's loop body, verbatim semantics
+            image = img[i:i + 1].cuda()
+            prefix = m.encode_image(image)
+            lpi, _ = m(image, cap_tok.cuda())
+            a = int(np.argmax(lpi.softmax(dim=-1).cpu().numpy(), axis=1)[0])
+            lpi, _ = m(image, vio_tok.cuda())
+            b = int(np.argmax(lpi.softmax(dim=-1).cpu().numpy(), axis=1)[0])
+            assert cosine_rows(out["clip_embedding"][i:i + 1].float().cpu(), prefix.float().cpu()).min() > 0.9999
+            assert out["captions"][i]["clip_embedding"] == i
+            assert out["captions"][i]["attribute"] == f"{cap_labels[a]} {vio_labels[b]} "
