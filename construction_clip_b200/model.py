@@ -286,6 +286,7 @@ class CLIP(nn.Module):
         self.text_projection = nn.Parameter(torch.empty(cfg.transformer_width, cfg.embed_dim))
         self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
         self._stores = {}
+        self.fp32_check_mode = False  # see set_fp32_check_mode
         self.initialize_parameters()
 
     # upstream's scheme (clip.model.CLIP.initialize_parameters)
@@ -332,9 +333,23 @@ class CLIP(nn.Module):
         return out
 
     # ---------------------------------------------------------------------------------- forward
+    def set_fp32_check_mode(self, on=True):
+        """Route the (inference) forward through the tensor-core-free fp32 kernels: fp32 activations
+        end to end, same bf16-representable weights.  Meets the 1e-4 logit tolerance of
+        BASELINE.json's "fp32 check mode"; ~50x slower, forward only."""
+        self.fp32_check_mode = bool(on)
+        return self
+
     def _features(self, which, inp):
         params = [p for _, p in self._tower_named_params(which)]
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        if self.fp32_check_mode:
+            if need_grad:
+                raise RuntimeError("fp32 check mode is forward only: call under torch.no_grad() / model.eval()")
+            store = self._store(which, inp.device)
+            store.sync()
+            fwd = T.vision_fwd_f32 if which == "visual" else T.text_fwd_f32
+            return fwd(store.W, self.cfg, inp)
         return _TowerFn.apply(self, which, need_grad, inp, *params)
 
     def encode_image(self, image):

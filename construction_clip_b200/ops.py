@@ -294,3 +294,37 @@ def adamw(master, param_bf16, grad, m, v, *, lr, beta1, beta2, eps, weight_decay
     L.check(L.load().b200clip_adamw(ctx, master.data_ptr(), _ptr(param_bf16), grad.data_ptr(), m.data_ptr(),
                                     v.data_ptr(), master.numel(), lr, beta1, beta2, eps, weight_decay, grad_scale,
                                     step, _ptr(hyper), st), "adamw")
+
+
+# ------------------------------------------------------------------------------ fp32 check mode
+def check_gemm_f32(a, w, *, b_major=L.MAJOR_K, bias=None, residual=None, quickgelu=False):
+    """fp32 SIMT GEMM of the check mode: a fp32 [M,K]; w bf16 [N,K] (MAJOR_K) or [K,N] (MAJOR_MN)."""
+    assert a.dtype == f32 and w.dtype == bf16
+    M, K = a.shape
+    N = w.shape[0] if b_major == L.MAJOR_K else w.shape[1]
+    out = torch.empty((M, N), device=a.device, dtype=f32)
+    ctx, st = _ctx_stream(a)
+    L.check(L.load().b200clip_check_gemm_f32(ctx, a.data_ptr(), _row_major(a, "a"), w.data_ptr(), _row_major(w, "w"),
+                                             b_major, _ptr(bias), _ptr(residual),
+                                             _row_major(residual, "residual") if residual is not None else 0,
+                                             out.data_ptr(), N, M, N, K, 1 if quickgelu else 0, st), "check_gemm_f32")
+    return out
+
+
+def check_attn_fwd_f32(qkv, B, S, H, causal):
+    assert qkv.dtype == f32 and qkv.is_contiguous()
+    out = torch.empty((B * S, H * 64), device=qkv.device, dtype=f32)
+    ctx, st = _ctx_stream(qkv)
+    L.check(L.load().b200clip_check_attn_fwd_f32(ctx, qkv.data_ptr(), out.data_ptr(), B, S, H, 1 if causal else 0, st),
+            "check_attn_fwd_f32")
+    return out
+
+
+def check_im2col_f32(image, patch, ldcols):
+    B, _, R, _ = image.shape
+    g = R // patch
+    cols = torch.empty((B * g * g, ldcols), device=image.device, dtype=f32)
+    ctx, st = _ctx_stream(image)
+    L.check(L.load().b200clip_check_im2col_f32(ctx, image.data_ptr(), cols.data_ptr(), ldcols, B, R, patch, st),
+            "check_im2col_f32")
+    return cols

@@ -205,3 +205,45 @@ def text_bwd(W, G, cfg, saved: TowerSaved, dfeat):
                            pooled, mean, rstd)
     dx = blocks_bwd(W, G, "transformer.", cfg.transformer_layers, dx, B, S, H, True, saved)
     O.embed_tokens_bwd(e["ids"], dx, G["token_embedding.weight"], G["positional_embedding"])
+
+
+# ------------------------------------------------------------------------------------------------
+# fp32 check mode: the same forward with fp32 activations and tensor-core-free fp32 kernels
+# (BASELINE.json: logits within 1e-4 of the reference in an fp32 check mode).  Forward only.
+def _blocks_fwd_f32(W, prefix, layers, x, B, S, H, causal):
+    for i in range(layers):
+        p = _blk(prefix, i)
+        h1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"], out_dtype=f32)
+        qkv = O.check_gemm_f32(h1, W[p + "attn.in_proj_weight"], bias=W[p + "attn.in_proj_bias"])
+        a = O.check_attn_fwd_f32(qkv, B, S, H, causal)
+        x = O.check_gemm_f32(a, W[p + "attn.out_proj.weight"], bias=W[p + "attn.out_proj.bias"], residual=x)
+        h2 = O.layernorm_fwd(x, W[p + "ln_2.weight"], W[p + "ln_2.bias"], out_dtype=f32)
+        g = O.check_gemm_f32(h2, W[p + "mlp.c_fc.weight"], bias=W[p + "mlp.c_fc.bias"], quickgelu=True)
+        x = O.check_gemm_f32(g, W[p + "mlp.c_proj.weight"], bias=W[p + "mlp.c_proj.bias"], residual=x)
+    return x
+
+
+def vision_fwd_f32(W, cfg, image):
+    B = image.shape[0]
+    p, n, d = cfg.vision_patch_size, cfg.vision_tokens, cfg.vision_width
+    kpad = W["conv1.weight"].shape[1]
+    cols = O.check_im2col_f32(image.float().contiguous(), p, kpad)
+    patch = O.check_gemm_f32(cols, W["conv1.weight"])
+    g2 = n - 1
+    ridx = torch.arange(-1, g2, device=image.device, dtype=i32).repeat(B, 1)
+    ridx[:, 1:] += (torch.arange(B, device=image.device, dtype=i32) * g2)[:, None]
+    x = O.layernorm_fwd(patch, W["ln_pre.weight"], W["ln_pre.bias"], rows=B * n, row_index=ridx.reshape(-1),
+                        neg_row=W["class_embedding"], add=W["positional_embedding"], add_period=n, out_dtype=f32)
+    x = _blocks_fwd_f32(W, "transformer.", cfg.vision_layers, x, B, n, d // 64, False)
+    cls_rows = torch.arange(B, device=image.device, dtype=i32) * n
+    pooled = O.layernorm_fwd(x, W["ln_post.weight"], W["ln_post.bias"], row_index=cls_rows, out_dtype=f32)
+    return O.check_gemm_f32(pooled, W["proj"], b_major=L.MAJOR_MN)
+
+
+def text_fwd_f32(W, cfg, text):
+    B, S = text.shape
+    ids = text.to(i32).contiguous()
+    x, eot = O.embed_tokens_fwd(ids, W["token_embedding.weight"], W["positional_embedding"], out_dtype=f32)
+    x = _blocks_fwd_f32(W, "transformer.", cfg.transformer_layers, x, B, S, cfg.transformer_heads, True)
+    pooled = O.layernorm_fwd(x, W["ln_final.weight"], W["ln_final.bias"], row_index=eot, out_dtype=f32)
+    return O.check_gemm_f32(pooled, W["text_projection"], b_major=L.MAJOR_MN)

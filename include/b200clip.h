@@ -203,6 +203,22 @@ int b200clip_clip_loss_bwd(b200clip_ctx* ctx, const float* img_all, const float*
                            int64_t Bl, int64_t Bg, int64_t E, float* d_img, float* d_txt, float* d_logit_scale,
                            void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---- fp32 check mode (forward only; BASELINE: logits within 1e-4 of the reference) --------------------
+ * Plain SIMT fp32 kernels with fp32 activations end to end; weights / biases are the bf16 values of
+ * the fast path, upcast exactly.  Together with b200clip_layernorm_fwd (f32 in / f32 out),
+ * b200clip_embed_tokens_fwd (f32 out), b200clip_l2norm_fwd and b200clip_logits they form a second,
+ * tensor-core-free implementation of the forward used to validate the model wiring to 1e-4. */
+/* C[M,N] = quickgelu?(A[M,K] . B(n,k) + bias[n]) + residual[M,N]; B bf16 [N,K] (MAJOR_K) or [K,N] (MAJOR_MN). */
+int b200clip_check_gemm_f32(b200clip_ctx* ctx, const float* A, int64_t lda, const void* B_bf16, int64_t ldb,
+                            int b_major, const void* bias_bf16, const float* residual, int64_t ldres, float* C,
+                            int64_t ldc, int64_t M, int64_t N, int64_t K, int quickgelu, void* stream);
+/* qkv fp32 [B*S, 3*H*64] -> out fp32 [B*S, H*64]; S <= 1024. */
+int b200clip_check_attn_fwd_f32(b200clip_ctx* ctx, const float* qkv, float* out, int64_t B, int64_t S, int64_t H,
+                                int causal, void* stream);
+/* image fp32 [B,3,R,R] -> cols fp32 [B*g*g, ldcols] (columns >= 3*p*p zero filled). */
+int b200clip_check_im2col_f32(b200clip_ctx* ctx, const float* image, float* cols, int64_t ldcols, int64_t B, int64_t R,
+                              int64_t patch, void* stream);
+
 /* ---- AdamW step (CLIP/train.py:143,169) on flat buffers: fp32 master weights, bf16 shadow -------
  * p -= lr * (m_hat / (sqrt(v_hat) + eps) + wd * p);  grad fp32 (multiplied by grad_scale).
  * hyper_dev: optional DEVICE float[3] = {lr, 1 - beta1^step, 1 - beta2^step}; when non-NULL it overrides

@@ -368,3 +368,25 @@ def test_batched_prefix_extraction_matches_per_image_loop(tmp_path):
             assert cosine_rows(out["clip_embedding"][i:i + 1].float().cpu(), prefix.float().cpu()).min() > 0.9999
             assert out["captions"][i]["clip_embedding"] == i
             assert out["captions"][i]["attribute"] == f"{cap_labels[a]} {vio_labels[b]} "
+
+
+def test_fp32_check_mode_logits_within_1e4():
+    """BASELINE.json: logits within 1e-4 abs in an fp32 check mode (config 1: 32 images x 16 prompts)."""
+    from oracle import clip_oracle as O
+    name = "ViT-B/32"
+    orc = oracle_model(name)
+    img, tok = _inputs(name, 32, 16, 12)
+    with torch.no_grad():
+        lpi_ref, _ = orc(img, tok)
+        fi_ref = orc.encode_image(img)
+    m = device_model(name, orc).eval().set_fp32_check_mode(True)
+    with torch.no_grad():
+        lpi, lpt = m(img.cuda(), tok.cuda())
+        fi = m.encode_image(img.cuda())
+    err = (lpi.float().cpu() - lpi_ref).abs().max().item()
+    assert err <= 1e-4, f"fp32 check mode logits max abs err {err}"
+    assert torch.equal(lpi.float().cpu().argmax(1), lpi_ref.argmax(1))
+    assert cosine_rows(fi.float().cpu(), fi_ref).min() >= 0.99999
+    with pytest.raises(RuntimeError, match="forward only"):
+        m.train()
+        m(img[:2].cuda(), tok[:2].cuda())
