@@ -6,11 +6,11 @@
 // `x @ visual.proj`, `x @ text_projection` and their autograd dgrad / wgrad
 // (reference call sites: CLIP/train.py:161 forward, CLIP/train.py:168 backward).
 //
-// One persistent CTA per SM, 18 warps:
-//   warp 0      TMA producer (one elected lane)
-//   warp 1      TMEM allocator + MMA issuer (one elected lane)
-//   warps 2-17  epilogue: warp w drains TMEM lane quadrant w%4 (32 rows of the 128-row tile) for one
-//               quarter of the tile's columns, transposing through shared memory so that every global
+// One persistent CTA per SM, 10 warps:
+//   warp 0     TMA producer (one elected lane)
+//   warp 1     TMEM allocator + MMA issuer (one elected lane)
+//   warps 2-9  epilogue: warp w drains TMEM lane quadrant w%4 (32 rows of the 128-row tile) for one
+//              half of the tile's columns, transposing through shared memory so that every global
 //              access (aux load, C store) is a full 128-byte row segment
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty pair (MMA <-> epilogue).
 #include <type_traits>
@@ -23,12 +23,10 @@ namespace b200 {
 constexpr int BM = 128;           // tile rows  (UMMA M, cta_group::1)
 constexpr int BK = 64;            // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;        // fixed for 16-bit inputs
-constexpr int kEpiWarps = 16;      // four warps per TMEM lane quadrant, each drains a quarter of the tile's columns
-constexpr int kEpiSplit = kEpiWarps / 4;
-constexpr int kBlk = 16;           // epilogue block: 32 rows x 16 fp32 columns
+constexpr int kEpiWarps = 8;       // two warps per TMEM lane quadrant, each takes half of the tile's columns
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kStageBytesA = BM * BK * 2;  // 16 KB
-constexpr int kEpiStageBytes = 32 * kBlk * 4;  // per-warp staging: 32 rows x 64 B, XOR-swizzled
+constexpr int kEpiStageBytes = 32 * 128;   // per-warp staging: 32 rows x 128 B, XOR-swizzled
 
 template <int BN>
 struct GemmCfg {
@@ -56,20 +54,15 @@ struct GemmParams {
 // ------------------------------------------------------------------------------------------------
 // Epilogue.  TMEM hands each thread one accumulator ROW (lane = row); writing rows straight to
 // global memory would make every warp-level access touch 32 different lines.  Each epilogue warp
-// therefore transposes 32 x 16 fp32 accumulator blocks through a private 2 KB shared-memory tile
-// (16-byte chunks XOR-swizzled: both access patterns are bank-conflict free) and does ALL the
-// epilogue maths in the coalesced layout, where a lane owns 4 consecutive columns of 4 different
-// rows (4 lanes = one 64-byte row segment = whole 32-byte sectors).  The epilogue of a tile is
-// latency bound (TMEM load -> transpose -> MUFU chain -> store), so it is spread over 16 warps: bias is loaded once per block into registers, aux (fp32 residual stream or the
+// therefore transposes 32 x 32 fp32 accumulator blocks through a private 4 KB shared-memory tile
+// (16-byte chunks XOR-swizzled with the row: both access patterns are bank-conflict free) and does
+// ALL the epilogue maths in the coalesced layout, where a lane owns 4 consecutive columns of 8
+// different rows: bias is loaded once per block into registers, aux (fp32 residual stream or the
 // saved bf16 pre-activation) is read with coalesced loads issued before the transpose, and the
 // result leaves as 8/16-byte stores that cover whole 32-byte sectors.
 // The tcgen05.ld of a block is in flight while its aux / bias loads are issued.
-// staging tile: 32 rows x 64 B (16 fp32).  Two rows share a 128-byte line; the 16-byte chunk index is
-// XORed with the line index so that both the row-layout writes (8 consecutive rows, same chunk) and
-// the coalesced reads (2 rows x 4 chunks) touch each bank once.
 __device__ __forceinline__ uint32_t stage_off(int row, int chunk) {
-    const int line = row >> 1;
-    return static_cast<uint32_t>(line * 128 + (row & 1) * 64 + ((chunk ^ (line & 3)) << 4));
+    return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -104,30 +97,30 @@ template <int EPI, bool OUT_F32>
 struct EpiOperands {
     static constexpr bool AUX_F32 = (EPI == B200CLIP_EPI_RESIDUAL) && OUT_F32;
     static constexpr bool AUX_BF16 = (EPI == B200CLIP_EPI_QUICKGELU_BWD) || (EPI == B200CLIP_EPI_RESIDUAL && !OUT_F32);
-    uint4 auxf[AUX_F32 ? 4 : 1];
-    uint2 auxh[AUX_BF16 ? 4 : 1];
+    uint4 auxf[AUX_F32 ? 8 : 1];
+    uint2 auxh[AUX_BF16 ? 8 : 1];
     float b0, b1, b2, b3;
 
     // Loads are UNCONDITIONAL from clamped (always valid) addresses so that all eight are in flight
     // at once -- a `cond ? load : 0` select puts a dependent MOV behind every load and serialises
     // them.  Values fetched for out-of-range rows / columns are never stored.
     __device__ __forceinline__ void load(const GemmParams& p, int m_base, int col0, int lane) {
-        const int rrow = lane >> 2;
-        int col = col0 + (lane & 3) * 4;
+        const int rrow = lane >> 3;
+        int col = col0 + (lane & 7) * 4;
         col = col < p.N ? col : 0;  // N % 8 == 0 and col % 4 == 0: the 4 columns are all in or all out
         if constexpr (AUX_F32) {
             const float* ap = reinterpret_cast<const float*>(p.aux) + col;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int grow = min(m_base + 8 * i + rrow, p.M - 1);
+            for (int i = 0; i < 8; ++i) {
+                const int grow = min(m_base + 4 * i + rrow, p.M - 1);
                 auxf[i] = *reinterpret_cast<const uint4*>(ap + static_cast<int64_t>(grow) * p.ldaux);
             }
         }
         if constexpr (AUX_BF16) {
             const __nv_bfloat16* ap = p.aux + col;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int grow = min(m_base + 8 * i + rrow, p.M - 1);
+            for (int i = 0; i < 8; ++i) {
+                const int grow = min(m_base + 4 * i + rrow, p.M - 1);
                 auxh[i] = *reinterpret_cast<const uint2*>(ap + static_cast<int64_t>(grow) * p.ldaux);
             }
         }
@@ -145,15 +138,15 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
                                                int m_base, int col0, float scale, uint8_t* stg, int lane) {
     using Op = EpiOperands<EPI, OUT_F32>;
     using OutT = typename std::conditional<OUT_F32, float, __nv_bfloat16>::type;
-    const int rrow = lane >> 2, rch = lane & 3;
+    const int rrow = lane >> 3, rch = lane & 7;
     const int col = col0 + rch * 4;
     const bool col_ok = col < p.N;
-    uint32_t acc[16];
-    tmem_ld_32x16(taddr, acc);
+    uint32_t acc[32];
+    tmem_ld_32x32(taddr, acc);
     tmem_ld_wait();
     // ---- transpose: row layout -> staging
 #pragma unroll
-    for (int c = 0; c < 4; ++c)
+    for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) = make_uint4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
     __syncwarp();
     // ---- coalesced layout: maths + stores.  Row pointers advance by a constant stride (no per-row
@@ -161,12 +154,12 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
     const int64_t first = static_cast<int64_t>(m_base + rrow) * p.ldc + col;
     OutT* cptr = reinterpret_cast<OutT*>(p.C) + first;
     [[maybe_unused]] __nv_bfloat16* pptr = (EPI == B200CLIP_EPI_QUICKGELU && p.preact != nullptr) ? p.preact + first : nullptr;
-    const int64_t rstride = 8 * p.ldc;
-    const int rows_left = col_ok ? (p.M - m_base - rrow + 7) >> 3 : 0;  // number of valid i (rows m_base+rrow+8i < M)
+    const int64_t rstride = 4 * p.ldc;
+    const int rows_left = col_ok ? (p.M - m_base - rrow + 3) >> 2 : 0;  // number of valid i (rows m_base+rrow+4i < M)
     [[maybe_unused]] float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int row = 8 * i + rrow;
+    for (int i = 0; i < 8; ++i) {
+        const int row = 4 * i + rrow;
         const uint4 v = *reinterpret_cast<const uint4*>(stg + stage_off(row, rch));
         float x0 = fmaf(__uint_as_float(v.x), scale, op.b0), x1 = fmaf(__uint_as_float(v.y), scale, op.b1);
         float x2 = fmaf(__uint_as_float(v.z), scale, op.b2), x3 = fmaf(__uint_as_float(v.w), scale, op.b3);
@@ -206,13 +199,12 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
     }
     if constexpr (EPI == B200CLIP_EPI_QUICKGELU_BWD) {
         if (p.colsum != nullptr) {  // warp-uniform
-            // lanes with equal (lane & 3) hold the same 4 columns for different rows
-#pragma unroll
-            for (int o = 4; o < 32; o <<= 1) {
-                cs0 += __shfl_xor_sync(0xffffffffu, cs0, o); cs1 += __shfl_xor_sync(0xffffffffu, cs1, o);
-                cs2 += __shfl_xor_sync(0xffffffffu, cs2, o); cs3 += __shfl_xor_sync(0xffffffffu, cs3, o);
-            }
-            if (lane < 4 && col_ok) red_add_v4(p.colsum + col, cs0, cs1, cs2, cs3);
+            // lanes l, l^8, l^16, l^24 hold the same 4 columns for different rows
+            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
+            cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
+            cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
+            cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
+            if (lane < 8 && col_ok) red_add_v4(p.colsum + col, cs0, cs1, cs2, cs3);
         }
     }
     __syncwarp();  // the staging tile is rewritten by the next block
@@ -223,16 +215,16 @@ template <int BN, int EPI, bool OUT_F32, bool ATOMIC>
 __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
                                            uint64_t* tmem_empty_bar, uint8_t* stg, int warp, int lane, int num_work) {
     const int quad = warp & 3;         // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;  // which quarter of the tile's columns this warp drains
+    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
     const float scale = (p.scale != nullptr) ? __ldg(p.scale) : 1.0f;
     int as = 0;
     uint32_t aphase = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
         const int tile = w / p.split_k;
         const int m_base = (tile / p.num_n_tiles) * BM + quad * 32;
-        const int n_base = (tile % p.num_n_tiles) * BN + half * (BN / kEpiSplit);
-        int nblk = (BN / kEpiSplit) / kBlk;
-        const int valid = (p.N - n_base + kBlk - 1) / kBlk;  // blocks with at least one real column (warp-uniform)
+        const int n_base = (tile % p.num_n_tiles) * BN + half * (BN / 2);
+        int nblk = (BN / 2) >> 5;
+        const int valid = (p.N - n_base + 31) >> 5;  // blocks with at least one real column (warp-uniform)
         if (valid < nblk) nblk = valid;
         EpiOperands<EPI, OUT_F32> opA, opB;  // ping-pong: the next block's operands load while this one runs
         if (nblk > 0) opA.load(p, m_base, n_base, lane);  // before waiting for the accumulator
@@ -240,15 +232,15 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
         __syncwarp();
         tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                               static_cast<uint32_t>(as * BN + half * (BN / kEpiSplit));
+                               static_cast<uint32_t>(as * BN + half * (BN / 2));
 #pragma unroll 1
         for (int j = 0; j < nblk; j += 2) {
-            if (j + 1 < nblk) opB.load(p, m_base, n_base + (j + 1) * kBlk, lane);
-            epilogue_block<EPI, OUT_F32, ATOMIC>(p, opA, taddr + j * kBlk, m_base, n_base + j * kBlk, scale, stg, lane);
+            if (j + 1 < nblk) opB.load(p, m_base, n_base + (j + 1) * 32, lane);
+            epilogue_block<EPI, OUT_F32, ATOMIC>(p, opA, taddr + j * 32, m_base, n_base + j * 32, scale, stg, lane);
             if (j + 1 < nblk) {
-                if (j + 2 < nblk) opA.load(p, m_base, n_base + (j + 2) * kBlk, lane);
-                epilogue_block<EPI, OUT_F32, ATOMIC>(p, opB, taddr + (j + 1) * kBlk, m_base, n_base + (j + 1) * kBlk,
-                                                     scale, stg, lane);
+                if (j + 2 < nblk) opA.load(p, m_base, n_base + (j + 2) * 32, lane);
+                epilogue_block<EPI, OUT_F32, ATOMIC>(p, opB, taddr + (j + 1) * 32, m_base, n_base + (j + 1) * 32, scale,
+                                                     stg, lane);
             }
         }
         tc_fence_before();
