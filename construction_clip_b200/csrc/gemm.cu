@@ -299,52 +299,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     if (warp == 0) {
         // ===================================== TMA producer =====================================
-        // The shared-memory ring holds 4 k-blocks (192 KB): with a DRAM-latency load that is not enough
-        // to keep the MMA pipe fed (measured ~675 cycles per k-block instead of 512).  The producer
-        // therefore also issues L2 PREFETCHES kPrefetch k-blocks ahead (across tile boundaries), which
-        // cost no shared memory: by the time the real load is issued its box is already in L2.
         if (lane == 0) {
-            constexpr int kPrefetch = 8;
-            auto coords = [&](int w, int& m0, int& n0, int& kb0, int& kb1) {
-                const int split = w % p.split_k;
-                const int tile = w / p.split_k;
-                m0 = (tile / p.num_n_tiles) * BM;
-                n0 = (tile % p.num_n_tiles) * BN;
-                kb0 = split * p.kb_per_split;
-                kb1 = min(p.kb_total, kb0 + p.kb_per_split);
-            };
-            auto prefetch = [&](int m0, int n0, int kb) {
-                if constexpr (!A_MN) {
-                    tma_prefetch_2d(&tmA, kb * BK, m0);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < BM / 64; ++j) tma_prefetch_2d(&tmA, m0 + 64 * j, kb * BK);
-                }
-                if constexpr (!B_MN) {
-                    tma_prefetch_2d(&tmB, kb * BK, n0);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < BN / 64; ++j) tma_prefetch_2d(&tmB, n0 + 64 * j, kb * BK);
-                }
-            };
             int stage = 0;
             uint32_t phase = 0;
-            // prefetch cursor: runs kPrefetch k-blocks ahead of the load cursor
-            int pw = blockIdx.x, pm0 = 0, pn0 = 0, pkb = 0, pkb1 = 0;
-            if (pw < num_work) coords(pw, pm0, pn0, pkb, pkb1);
-            int ahead = 0;
             for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
-                int m0, n0, kb0, kb1;
-                coords(w, m0, n0, kb0, kb1);
+                const int split = w % p.split_k;
+                const int tile = w / p.split_k;
+                const int m0 = (tile / p.num_n_tiles) * BM;
+                const int n0 = (tile % p.num_n_tiles) * BN;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
-                    while (ahead < kPrefetch && pw < num_work) {
-                        prefetch(pm0, pn0, pkb);
-                        ++ahead;
-                        if (++pkb == pkb1) {
-                            pw += gridDim.x;
-                            if (pw < num_work) coords(pw, pm0, pn0, pkb, pkb1);
-                        }
-                    }
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                     uint8_t* sA = smem + stage * Cfg::kStageBytes;
@@ -363,7 +328,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         for (int j = 0; j < BN / 64; ++j)
                             tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
                     }
-                    --ahead;
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
