@@ -13,6 +13,7 @@
 //              half of the tile's columns, transposing through shared memory so that every global
 //              access (aux load, C store) is a full 128-byte row segment
 // Pipelines: smem full/empty ring (TMA <-> MMA), TMEM full/empty pair (MMA <-> epilogue).
+#include <cstdlib>
 #include <type_traits>
 
 #include "common.cuh"
@@ -534,7 +535,11 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
 
     // tile width: 256 when that still fills the machine, else 128 for more CTAs
     const int64_t tiles256 = ceil_div(M, BM) * ceil_div(N, 256);
-    const bool use256 = (N >= 256) && (tiles256 >= ctx->num_sms || (out_f32 && epilogue == B200CLIP_EPI_NONE));
+    bool use256 = (N >= 256) && (tiles256 >= ctx->num_sms || (out_f32 && epilogue == B200CLIP_EPI_NONE));
+    if (const char* f = getenv("B200CLIP_FORCE_BN")) {  // tuning / experiments only
+        if (atoi(f) == 128) use256 = false;
+        if (atoi(f) == 256 && N >= 256) use256 = true;
+    }
     const int64_t tiles = use256 ? tiles256 : ceil_div(M, BM) * ceil_div(N, 128);
     if (split_k <= 0) split_k = out_f32 ? choose_split_k(tiles, p.kb_total, ctx->num_sms) : 1;
     if (split_k > p.kb_total) split_k = p.kb_total;
