@@ -212,7 +212,10 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
 }
 
 // The whole persistent loop of one epilogue warp, specialised on the epilogue flavour.
-template <int BN, int EPI, bool OUT_F32, bool ATOMIC>
+// PAIR = true: the CTA is one half of a cta_group::2 pair working on a 256-row tile; it owns rows
+// [rank*128, rank*128+128) of the tile, iterates over the work list of its CLUSTER and releases the
+// accumulator stage on the LEADER CTA's barrier.
+template <int BN, int EPI, bool OUT_F32, bool ATOMIC, bool PAIR = false>
 __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
                                            uint64_t* tmem_empty_bar, uint8_t* stg, int warp, int lane, int num_work) {
     const int quad = warp & 3;         // TMEM lane quadrant this warp may access
@@ -220,9 +223,12 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
     const float scale = (p.scale != nullptr) ? __ldg(p.scale) : 1.0f;
     int as = 0;
     uint32_t aphase = 0;
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+    const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+    const int w0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+    const int wstep = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    for (int w = w0; w < num_work; w += wstep) {
         const int tile = w / p.split_k;
-        const int m_base = (tile / p.num_n_tiles) * BM + quad * 32;
+        const int m_base = (tile / p.num_n_tiles) * (PAIR ? 2 * BM : BM) + rank * BM + quad * 32;
         const int n_base = (tile % p.num_n_tiles) * BN + half * (BN / 2);
         int nblk = (BN / 2) >> 5;
         const int valid = (p.N - n_base + 31) >> 5;  // blocks with at least one real column (warp-uniform)
@@ -246,7 +252,12 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+        if (lane == 0) {
+            if constexpr (PAIR)
+                mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[as]), 0));  // the leader's barrier
+            else
+                mbar_arrive(&tmem_empty_bar[as]);
+        }
         if (++as == 2) {
             as = 0;
             aphase ^= 1u;
@@ -411,6 +422,207 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
+// CTA-pair GEMM (tcgen05 cta_group::2): two CTAs of a cluster compute one 256 x 256 tile.  Each CTA
+// loads its own 128 rows of A and HALF of the B tile (128 of the 256 columns); the pair's tensor cores
+// read both halves, so the operand bytes per flop fed through L2 / shared memory drop by a third
+// against the 128 x 256 single-CTA tile -- the measured limiter of that kernel -- and a stage shrinks
+// to 32 KB, which buys a 6-deep ring.  Only the leader CTA (cluster rank 0) issues MMAs; full barriers
+// live in the leader (both CTAs' TMA transactions and producer arrivals are routed to it), empty /
+// accumulator-full barriers are signalled in both CTAs with a multicast tcgen05.commit, and both
+// epilogues release the accumulator on the leader's barrier.
+constexpr int kStageBytesPair = 2 * (BM * BK * 2);  // A 16 KB + half of B 16 KB
+constexpr int kStagesPair = 6;
+constexpr int kSmemBytesPair = kStagesPair * kStageBytesPair + kEpiWarps * kEpiStageBytes + 1024;
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_pair_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+    constexpr int BN = 256;
+    constexpr int kStages = kStagesPair;
+    extern __shared__ uint8_t smem_raw[];
+    __shared__ uint64_t full_bar[kStages];
+    __shared__ uint64_t empty_bar[kStages];
+    __shared__ uint64_t tmem_full_bar[2];
+    __shared__ uint64_t tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int rank = static_cast<int>(cluster_ctarank());
+    const bool leader = rank == 0;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmA);
+        prefetch_tmap(&tmB);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 2);   // leader: its own arrive.expect_tx + the peer producer's arrive
+            mbar_init(&empty_bar[s], 1);  // multicast commit of the leader's MMA warp
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tmem_full_bar[s], 1);
+            mbar_init(&tmem_empty_bar[s], 2 * kEpiWarps);  // leader: every epilogue warp of both CTAs
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(&tmem_base_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_base_slot;
+
+    const int num_work = p.num_m_tiles * p.num_n_tiles * p.split_k;  // num_m_tiles counts 256-row tiles
+    const int w0 = static_cast<int>(blockIdx.x >> 1), wstep = static_cast<int>(gridDim.x >> 1);
+
+    if (warp == 0) {
+        // ================== TMA producer (both CTAs: own A rows, own half of B) ==================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = w0; w < num_work; w += wstep) {
+                const int split = w % p.split_k;
+                const int tile = w / p.split_k;
+                const int m0 = (tile / p.num_n_tiles) * (2 * BM) + rank * BM;
+                const int n0 = (tile % p.num_n_tiles) * BN + rank * (BN / 2);
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    if (leader)
+                        mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytesPair);
+                    else
+                        mbar_arrive_cluster(mapa_shared(smem_u32(&full_bar[stage]), 0));
+                    uint8_t* sA = smem + stage * kStageBytesPair;
+                    uint8_t* sB = sA + kStageBytesA;
+                    if constexpr (!A_MN) {
+                        tma_load_2d_2sm(sA, &tmA, &full_bar[stage], kb * BK, m0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            tma_load_2d_2sm(sA + j * (BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, kb * BK);
+                    }
+                    if constexpr (!B_MN) {
+                        tma_load_2d_2sm(sB, &tmB, &full_bar[stage], kb * BK, n0);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 2; ++j)
+                            tma_load_2d_2sm(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
+                    }
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================== MMA issuer (leader CTA only) ==================
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int w = w0; w < num_work; w += wstep) {
+                const int split = w % p.split_k;
+                const int kb0 = split * p.kb_per_split;
+                const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+                mbar_wait(&tmem_empty_bar[as], aphase ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(as * BN);
+                for (int kb = kb0; kb < kb1; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(smem + stage * kStageBytesPair);
+                    const uint32_t sB = sA + kStageBytesA;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t da = A_MN ? make_smem_desc_sw128(sA + k * (UMMA_K * 128), BK * 128, 1024)
+                                                 : make_smem_desc_sw128(sA + k * (UMMA_K * 2), 16, 1024);
+                        const uint64_t db = B_MN ? make_smem_desc_sw128(sB + k * (UMMA_K * 128), BK * 128, 1024)
+                                                 : make_smem_desc_sw128(sB + k * (UMMA_K * 2), 16, 1024);
+                        umma_bf16_2sm(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit_2sm(&empty_bar[stage], 3);  // frees this slot in BOTH CTAs
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit_2sm(&tmem_full_bar[as], 3);  // accumulators complete -> both epilogues
+                if (++as == 2) {
+                    as = 0;
+                    aphase ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ================== epilogue warps (both CTAs drain their own 128 rows) ==================
+        uint8_t* stg = smem + kStages * kStageBytesPair + (warp - 2) * kEpiStageBytes;
+#define EPI_LOOP(E, F32, AT) \
+    epilogue_loop<BN, E, F32, AT, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, stg, warp, lane, num_work)
+        if (p.out_f32) {
+            if (p.atomic_out)
+                EPI_LOOP(B200CLIP_EPI_NONE, true, true);
+            else if (p.epilogue == B200CLIP_EPI_RESIDUAL)
+                EPI_LOOP(B200CLIP_EPI_RESIDUAL, true, false);
+            else
+                EPI_LOOP(B200CLIP_EPI_NONE, true, false);
+        } else {
+            switch (p.epilogue) {
+                case B200CLIP_EPI_QUICKGELU: EPI_LOOP(B200CLIP_EPI_QUICKGELU, false, false); break;
+                case B200CLIP_EPI_RESIDUAL: EPI_LOOP(B200CLIP_EPI_RESIDUAL, false, false); break;
+                case B200CLIP_EPI_QUICKGELU_BWD: EPI_LOOP(B200CLIP_EPI_QUICKGELU_BWD, false, false); break;
+                default: EPI_LOOP(B200CLIP_EPI_NONE, false, false); break;
+            }
+        }
+#undef EPI_LOOP
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // the peer's shared memory / TMEM must stay alive until the leader's MMAs are done
+    if (warp == 1) {
+        __syncwarp();
+        tmem_dealloc_2sm(tmem_base, 512);
+    }
+}
+
+template <bool A_MN, bool B_MN>
+static int set_attr_pair() {
+    cudaError_t e = cudaFuncSetAttribute(gemm_pair_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBytesPair);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(gemm pair): %s", cudaGetErrorString(e));
+        return B200CLIP_ERR_CUDA;
+    }
+    return 0;
+}
+
+template <bool A_MN, bool B_MN>
+static int launch_pair(b200clip_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p,
+                       cudaStream_t stream) {
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (!A_MN)
+        rc = make_tmap_bf16_2d(ctx, &tmA, A, p.K, p.M, lda, BK, BM);
+    else
+        rc = make_tmap_bf16_2d(ctx, &tmA, A, p.M, p.K, lda, 64, BK);
+    if (rc) return rc;
+    if (!B_MN)
+        rc = make_tmap_bf16_2d(ctx, &tmB, B, p.K, p.N, ldb, BK, 128);  // this CTA's half of the 256 columns
+    else
+        rc = make_tmap_bf16_2d(ctx, &tmB, B, p.N, p.K, ldb, 64, BK);
+    if (rc) return rc;
+    p.num_m_tiles = static_cast<int>(ceil_div(p.M, 2 * BM));
+    p.num_n_tiles = static_cast<int>(ceil_div(p.N, 256));
+    const int64_t work = static_cast<int64_t>(p.num_m_tiles) * p.num_n_tiles * p.split_k;
+    const int clusters = static_cast<int>(work < ctx->num_sms / 2 ? work : ctx->num_sms / 2);
+    gemm_pair_bf16_kernel<A_MN, B_MN><<<2 * clusters, kGemmThreads, kSmemBytesPair, stream>>>(tmA, tmB, p);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN>
 static int set_attr() {
     cudaError_t e = cudaFuncSetAttribute(gemm_bf16_kernel<BN, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -430,6 +642,9 @@ int init_gemm(b200clip_ctx*) {
     if ((rc = set_attr<128, false, false>())) return rc;
     if ((rc = set_attr<128, false, true>())) return rc;
     if ((rc = set_attr<128, true, true>())) return rc;
+    if ((rc = set_attr_pair<false, false>())) return rc;
+    if ((rc = set_attr_pair<false, true>())) return rc;
+    if ((rc = set_attr_pair<true, true>())) return rc;
     return 0;
 }
 
@@ -533,6 +748,15 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
     p.out_f32 = out_f32 ? 1 : 0;
     p.epilogue = epilogue;
 
+    // CTA-pair kernel (256 x 256 tiles over 74 clusters) when the problem has enough such tiles;
+    // B200CLIP_GEMM_PAIR=0 disables it (tuning / bisecting)
+    static const bool pair_enabled = [] {
+        const char* e = getenv("B200CLIP_GEMM_PAIR");
+        return !(e && atoi(e) == 0);
+    }();
+    const int clusters = ctx->num_sms / 2;
+    const int64_t tiles_pair = ceil_div(M, 2 * BM) * ceil_div(N, 256);
+    const bool use_pair = pair_enabled && N >= 256 && M >= 2 * BM && (tiles_pair >= clusters || (out_f32 && epilogue == B200CLIP_EPI_NONE));
     // tile width: 256 when that still fills the machine, else 128 for more CTAs
     const int64_t tiles256 = ceil_div(M, BM) * ceil_div(N, 256);
     bool use256 = (N >= 256) && (tiles256 >= ctx->num_sms || (out_f32 && epilogue == B200CLIP_EPI_NONE));
@@ -540,8 +764,8 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
         if (atoi(f) == 128) use256 = false;
         if (atoi(f) == 256 && N >= 256) use256 = true;
     }
-    const int64_t tiles = use256 ? tiles256 : ceil_div(M, BM) * ceil_div(N, 128);
-    if (split_k <= 0) split_k = out_f32 ? choose_split_k(tiles, p.kb_total, ctx->num_sms) : 1;
+    const int64_t tiles = use_pair ? tiles_pair : (use256 ? tiles256 : ceil_div(M, BM) * ceil_div(N, 128));
+    if (split_k <= 0) split_k = out_f32 ? choose_split_k(tiles, p.kb_total, use_pair ? clusters : ctx->num_sms) : 1;
     if (split_k > p.kb_total) split_k = p.kb_total;
     p.kb_per_split = static_cast<int>(ceil_div(p.kb_total, split_k));
     split_k = static_cast<int>(ceil_div(p.kb_total, p.kb_per_split));  // no empty splits
@@ -550,6 +774,11 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool amn = a_major == B200CLIP_MAJOR_MN, bmn = b_major == B200CLIP_MAJOR_MN;
+    if (use_pair) {
+        if (!amn && !bmn) return launch_pair<false, false>(ctx, A, lda, B, ldb, p, st);
+        if (!amn && bmn) return launch_pair<false, true>(ctx, A, lda, B, ldb, p, st);
+        return launch_pair<true, true>(ctx, A, lda, B, ldb, p, st);
+    }
     if (use256) {
         if (!amn && !bmn) return launch<256, false, false>(ctx, A, lda, B, ldb, p, st);
         if (!amn && bmn) return launch<256, false, true>(ctx, A, lda, B, ldb, p, st);

@@ -34,6 +34,7 @@ def _close(got, ref, atol, rtol, what=""):
 GEMM_SHAPES = [
     (128, 128, 64), (128, 256, 64), (128, 128, 256), (256, 512, 192), (1600, 2304, 768), (1232, 512, 2048),
     (77, 136, 72), (3000, 768, 3072), (32, 512, 768), (6400, 3072, 768),
+    (20000, 768, 512), (19999, 520, 200),   # CTA-pair (cta_group::2) kernel: >= 74 tiles of 256 x 256, ragged edges
 ]
 
 
@@ -68,9 +69,10 @@ def test_gemm_tn_wgrad(ops, M, N, K):
     _close(out, 2 * ref, 2e-3 * math.sqrt(K), 1e-3, f"gemm TN accumulate {M}x{N}x{K}")
 
 
-def test_gemm_epilogues(ops):
+@pytest.mark.parametrize("M", [1000, 20000])   # 20000 rows -> CTA-pair kernel
+def test_gemm_epilogues(ops, M):
     from construction_clip_b200 import lib as L
-    M, N, K = 1000, 768, 512
+    N, K = 768, 512
     a, w = _rand((M, K), seed=7), _rand((N, K), 0.05, seed=8)
     bias, aux = _rand((N,), seed=9), _rand((M, N), seed=10)
     base = a.float() @ w.float().t() + bias.float()
