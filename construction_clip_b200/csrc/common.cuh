@@ -182,8 +182,13 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t smem_addr, uint32_t cta
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
     return r;
 }
+// Remote arrive with the DEFAULT (cta-scope release) semantics, as CUTLASS' ClusterBarrier::arrive does.
+// A `.release.cluster` arrive compiles to an ERRBAR that waits for the thread's outstanding bulk
+// copies: in the pair GEMM's producer it serialised every k-block behind the previous TMA load
+// (measured: 650 instead of 1250 TFLOP/s).  The data hand-over does not need it: TMA bytes are
+// published by complete_tx, TMEM reads by tcgen05.fence::before_thread_sync.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // TMA load issued by either CTA of a pair; the transaction bytes are credited to the LEADER CTA's
 // barrier (peer bit of the shared::cluster address cleared, as CUTLASS' SM100_TMA_2SM_LOAD does)
