@@ -51,6 +51,27 @@ __device__ __forceinline__ uint8_t* p_chunk(uint8_t* base, int atom_bytes, int r
 
 __device__ __forceinline__ bool masked(int r, int c, int S, int causal) { return c >= S || (causal && c > r); }
 
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// sub-CTA barrier: `count` threads (a multiple of 32) meet on hardware barrier `id` (1..15; 0 = __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
+
+// Columns [0, lim) of score row r are attended: everything (lim = S) or the causal prefix; rows past the
+// sequence have none.  Score positions outside that range are masked in EVERY work item of a launch,
+// so the P / dS tiles are zeroed once and the masked positions are simply never written.
+__device__ __forceinline__ int row_limit(int r, int S, int causal) { return r >= S ? 0 : (causal ? r + 1 : S); }
+// the same bound for a whole warp (rows row0 .. row0 + 31): TMEM loads are warp-collective, so the
+// chunk loop runs to the warp-uniform bound and each thread masks inside it
+__device__ __forceinline__ int warp_limit(int row0, int S, int causal) {
+    return row0 >= S ? 0 : (causal ? min(S, row0 + 32) : S);
+}
+
 // ------------------------------------------------------------------------------------------------
 template <bool BIG>  // BIG: S > 64 (P needs two 64-column tiles)
 __global__ void __launch_bounds__(kAttnThreads)
@@ -95,14 +116,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
     const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
     const float sc = 0.125f * kLog2e;
     const int num_work = p.B * H;
+    const int lim = row_limit(r, S, p.causal);                        // attended columns of this row
+    const int wchunks = (warp_limit(warp * 32, S, p.causal) + 15) >> 4;  // 16-column chunks this warp visits
+    auto issue_loads = [&](int w) {
+        const int b = w / H, h = w - b * H;
+        mbar_arrive_expect_tx(&bar_load, load_bytes);
+        tma_load_2d(sQ, &tm_qkv, &bar_load, h * 64, b * S);
+        tma_load_2d(sK, &tm_qkv, &bar_load, d + h * 64, b * S);
+        tma_load_2d(sV, &tm_qkv, &bar_load, 2 * d + h * 64, b * S);
+    };
+    if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < num_work) issue_loads(blockIdx.x);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-        const int b = w / H, h = w % H;
+        const int b = w / H, h = w - b * H;
         if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(&bar_load, load_bytes);
-            tma_load_2d(sQ, &tm_qkv, &bar_load, h * 64, b * S);
-            tma_load_2d(sK, &tm_qkv, &bar_load, d + h * 64, b * S);
-            tma_load_2d(sV, &tm_qkv, &bar_load, 2 * d + h * 64, b * S);
             mbar_wait(&bar_load, it & 1u);
             tc_fence_after();
 #pragma unroll
@@ -113,40 +140,55 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
         }
         float sum = 1.f;
         if (warp_live) {
-        mbar_wait(&bar_mma, 0u);
-        __syncwarp();
-        tc_fence_after();
+            mbar_wait(&bar_mma, 0u);
+            __syncwarp();
+            tc_fence_after();
 
-        // ---- softmax over row r: pass 1 max, pass 2 exp / sum / write P ----
-        float mx = -INFINITY;
-        for (int c0 = 0; c0 < npad; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld_32x16(trow + c0, v);
-            tmem_ld_wait();
+            // ---- softmax over row r: pass 1 max, pass 2 exp / sum / write P ----
+            float mx = -INFINITY;
+            for (int ci = 0; ci < wchunks; ++ci) {
+                const int c0 = ci << 4;
+                uint32_t v[16];
+                __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-row branches
+                tmem_ld_32x16(trow + c0, v);
+                tmem_ld_wait();
+                if (c0 + 16 <= lim) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j)
-                if (!masked(r, c0 + j, S, p.causal)) mx = fmaxf(mx, __uint_as_float(v[j]));
-        }
-        sum = 0.f;
-        for (int c0 = 0; c0 < npad; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld_32x16(trow + c0, v);
-            tmem_ld_wait();
-            float e[16];
+                    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                } else {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-                e[j] = masked(r, c0 + j, S, p.causal) ? 0.f : exp2f((__uint_as_float(v[j]) - mx) * sc);
-                sum += e[j];
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < lim) mx = fmaxf(mx, __uint_as_float(v[j]));
+                }
             }
-            if (r < npad) {  // rows beyond the compact tile do not exist
-                *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, c0 >> 3)) =
-                    make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
-                *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, (c0 >> 3) + 1)) =
-                    make_uint4(pack_bf16(e[8], e[9]), pack_bf16(e[10], e[11]), pack_bf16(e[12], e[13]), pack_bf16(e[14], e[15]));
+            const float msc = mx * sc;
+            sum = 0.f;
+            for (int ci = 0; ci < wchunks; ++ci) {
+                const int c0 = ci << 4;
+                uint32_t v[16];
+                __syncwarp();
+                tmem_ld_32x16(trow + c0, v);
+                tmem_ld_wait();
+                if (c0 < lim) {  // else: masked in every work item, the tile position stays zero
+                    float e[16];
+                    if (c0 + 16 <= lim) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) e[j] = ex2_fast(fmaf(__uint_as_float(v[j]), sc, -msc));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            e[j] = (c0 + j < lim) ? ex2_fast(fmaf(__uint_as_float(v[j]), sc, -msc)) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum += e[j];
+                    *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, c0 >> 3)) = make_uint4(
+                        pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
+                    *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, (c0 >> 3) + 1)) = make_uint4(
+                        pack_bf16(e[8], e[9]), pack_bf16(e[10], e[11]), pack_bf16(e[12], e[13]), pack_bf16(e[14], e[15]));
+                }
             }
-        }
-        if (p.lse != nullptr && r < S)  // log2-domain: p = exp2(s * sc - lse)
-            p.lse[(static_cast<int64_t>(b) * H + h) * S + r] = mx * sc + log2f(sum);
+            if (p.lse != nullptr && r < S)  // log2-domain: p = exp2(s * sc - lse)
+                p.lse[(static_cast<int64_t>(b) * H + h) * S + r] = msc + log2f(sum);
         }  // warp_live
         fence_proxy_async_smem();
         tc_fence_before();
@@ -161,6 +203,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
         }
         if (warp_live) {
             mbar_wait(&bar_mma, 1u);
+            // every tile is free again: fetch the next work item under this one's epilogue
+            if (threadIdx.x == 0 && w + static_cast<int>(gridDim.x) < num_work) issue_loads(w + gridDim.x);
             __syncwarp();
             tc_fence_after();
             const float inv = 1.0f / sum;
@@ -358,6 +402,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_load, bar_mma;
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_D[2][128];  // the two column-half partial sums of D = rowsum(dO o O) per row
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S = p.S, H = p.H, npad = p.npad;
     const int TB = npad * 128;
@@ -399,29 +444,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const uint32_t idesc_tn = make_idesc_bf16(128, 64, 1, 1);     // dV = P^T dO, dK = dS^T Q
     const uint32_t idesc_nn = make_idesc_bf16(128, 64, 0, 1);     // dQ = dS K
     const float sc = 0.125f * kLog2e;
-    const int nchunks = npad >> 4;
-    const int ch0 = half == 0 ? 0 : (nchunks + 1) / 2;
-    const int ch1 = half == 0 ? (nchunks + 1) / 2 : nchunks;
     const int num_work = p.B * H;
+    const bool live = r < S;
+    const int lim = row_limit(r, S, p.causal);                               // attended columns of this row
+    const int wchunks = (warp_limit((warp & 3) * 32, S, p.causal) + 15) >> 4;  // 16-column chunks this warp pair visits
+    auto issue_loads = [&](int w) {
+        const int b = w / H, h = w - b * H;
+        mbar_arrive_expect_tx(&bar_load, load_bytes);
+        tma_load_2d(sQ, &tm_qkv, &bar_load, h * 64, b * S);
+        tma_load_2d(sK, &tm_qkv, &bar_load, d + h * 64, b * S);
+        tma_load_2d(sV, &tm_qkv, &bar_load, 2 * d + h * 64, b * S);
+        tma_load_2d(sdO, &tm_do, &bar_load, h * 64, b * S);
+    };
+    if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < num_work) issue_loads(blockIdx.x);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
-        const int b = w / H, h = w % H;
-        if (threadIdx.x == 0) {
-            mbar_arrive_expect_tx(&bar_load, load_bytes);
-            tma_load_2d(sQ, &tm_qkv, &bar_load, h * 64, b * S);
-            tma_load_2d(sK, &tm_qkv, &bar_load, d + h * 64, b * S);
-            tma_load_2d(sV, &tm_qkv, &bar_load, 2 * d + h * 64, b * S);
-            tma_load_2d(sdO, &tm_do, &bar_load, h * 64, b * S);
-        }
-        // row statistics from the forward, fetched while the tiles are in flight
-        const bool live = r < S;
+        const int b = w / H, h = w - b * H;
+        // row statistics from the forward, fetched while the tiles are in flight; the two threads of a
+        // row each take half of the 64 columns of D = rowsum(dO o O)
         float m2 = 0.f;
-        uint4 ov[8];
+        uint4 ov[4];
         if (live) {
             m2 = p.lse[(static_cast<int64_t>(b) * H + h) * S + r];
-            const uint4* op = reinterpret_cast<const uint4*>(p.o + (static_cast<int64_t>(b) * S + r) * d + h * 64);
+            const uint4* op =
+                reinterpret_cast<const uint4*>(p.o + (static_cast<int64_t>(b) * S + r) * d + h * 64) + half * 4;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) ov[c] = __ldg(op + c);
+            for (int c = 0; c < 4; ++c) ov[c] = __ldg(op + c);
         }
         if (threadIdx.x == 0) {
             mbar_wait(&bar_load, it & 1u);
@@ -439,48 +487,61 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         if (warp_live) {
             // D = rowsum(dO o O) while the tensor core works
             mbar_wait(&bar_load, it & 1u);
-            float D = 0.f;
+            float part = 0.f;
             if (live) {
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint4 dv = *reinterpret_cast<const uint4*>(sdO + r * 128 + ((c ^ (r & 7)) << 4));
+                for (int c = 0; c < 4; ++c) {
+                    const int cc = half * 4 + c;
+                    const uint4 dv = *reinterpret_cast<const uint4*>(sdO + r * 128 + ((cc ^ (r & 7)) << 4));
                     const uint32_t a[4] = {dv.x, dv.y, dv.z, dv.w}, o4[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float2 x = unpack_bf16(a[j]), y = unpack_bf16(o4[j]);
-                        D = fmaf(x.x, y.x, D);
-                        D = fmaf(x.y, y.y, D);
+                        part = fmaf(x.x, y.x, part);
+                        part = fmaf(x.y, y.y, part);
                     }
                 }
             }
+            s_D[half][r] = part;
+            named_bar_sync(1 + (warp & 3), 64);  // the two warps that share these 32 rows
+            const float D8 = (s_D[0][r] + s_D[1][r]) * 0.125f;
             mbar_wait(&bar_mma, 0u);
             __syncwarp();
             tc_fence_after();
 
-            // single pass: P = exp2(S*sc - lse), dS = P o (dP - D) / 8 -> swizzled smem (bf16)
-            for (int ci = ch0; ci < ch1; ++ci) {
+            // single pass: P = exp2(S*sc - lse), dS = P o (dP - D) / 8 -> swizzled smem (bf16); the two
+            // warps of a row group take alternate 16-column chunks
+            for (int ci = half; ci < wchunks; ci += 2) {
                 const int c0 = ci << 4;
                 uint32_t v[16], g[16];
+                __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-row branches
                 tmem_ld_32x16(trow + c0, v);
                 tmem_ld_32x16(trow + 128 + c0, g);
                 tmem_ld_wait();
-                float pe[16], ds[16];
+                if (c0 < lim) {  // else: masked in every work item, the tile positions stay zero
+                    float pe[16], ds[16];
+                    if (c0 + 16 <= lim) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const bool m = !live || masked(r, c0 + j, S, p.causal);
-                    const float e = m ? 0.f : exp2f(__uint_as_float(v[j]) * sc - m2);
-                    pe[j] = e;
-                    ds[j] = m ? 0.f : e * (__uint_as_float(g[j]) - D) * 0.125f;
-                }
-                if (r < npad) {
-                    *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, c0 >> 3)) =
-                        make_uint4(pack_bf16(pe[0], pe[1]), pack_bf16(pe[2], pe[3]), pack_bf16(pe[4], pe[5]), pack_bf16(pe[6], pe[7]));
-                    *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, (c0 >> 3) + 1)) =
-                        make_uint4(pack_bf16(pe[8], pe[9]), pack_bf16(pe[10], pe[11]), pack_bf16(pe[12], pe[13]), pack_bf16(pe[14], pe[15]));
-                    *reinterpret_cast<uint4*>(p_chunk(sdS, TB, r, c0 >> 3)) =
-                        make_uint4(pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
-                    *reinterpret_cast<uint4*>(p_chunk(sdS, TB, r, (c0 >> 3) + 1)) =
-                        make_uint4(pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]), pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
+                        for (int j = 0; j < 16; ++j) {
+                            pe[j] = ex2_fast(fmaf(__uint_as_float(v[j]), sc, -m2));
+                            ds[j] = pe[j] * fmaf(__uint_as_float(g[j]), 0.125f, -D8);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) {
+                            const bool ok = c0 + j < lim;
+                            pe[j] = ok ? ex2_fast(fmaf(__uint_as_float(v[j]), sc, -m2)) : 0.f;
+                            ds[j] = ok ? pe[j] * fmaf(__uint_as_float(g[j]), 0.125f, -D8) : 0.f;
+                        }
+                    }
+                    *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, c0 >> 3)) = make_uint4(
+                        pack_bf16(pe[0], pe[1]), pack_bf16(pe[2], pe[3]), pack_bf16(pe[4], pe[5]), pack_bf16(pe[6], pe[7]));
+                    *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, (c0 >> 3) + 1)) = make_uint4(
+                        pack_bf16(pe[8], pe[9]), pack_bf16(pe[10], pe[11]), pack_bf16(pe[12], pe[13]), pack_bf16(pe[14], pe[15]));
+                    *reinterpret_cast<uint4*>(p_chunk(sdS, TB, r, c0 >> 3)) = make_uint4(
+                        pack_bf16(ds[0], ds[1]), pack_bf16(ds[2], ds[3]), pack_bf16(ds[4], ds[5]), pack_bf16(ds[6], ds[7]));
+                    *reinterpret_cast<uint4*>(p_chunk(sdS, TB, r, (c0 >> 3) + 1)) = make_uint4(
+                        pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]), pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
                 }
             }
         }
@@ -509,6 +570,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
         if (warp_live) {
             mbar_wait(&bar_mma, 1u);
+            // every tile is free again: fetch the next work item under this one's epilogue
+            if (threadIdx.x == 0 && w + static_cast<int>(gridDim.x) < num_work) issue_loads(w + gridDim.x);
             __syncwarp();
             tc_fence_after();
             // six 32-column output chunks per row: dQ (TMEM 128..191), dK (64..127), dV (0..63);

@@ -286,6 +286,17 @@ __global__ void cast_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bflo
     for (int64_t i = (nv << 3) + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride)
         dst[i] = __float2bfloat16_rn(src[i]);
 }
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): two bf16 GEMM operands that together carry ~16 mantissa bits
+__global__ void split_f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ hi,
+                                         __nv_bfloat16* __restrict__ lo, int64_t n) {
+    const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+        const float x = src[i];
+        const __nv_bfloat16 h = __float2bfloat16_rn(x);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(x - __bfloat162float(h));
+    }
+}
 __global__ void cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst, int64_t n) {
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride)
@@ -468,6 +479,16 @@ extern "C" int b200clip_cast_f32_to_bf16(b200clip_ctx* ctx, const float* src, vo
                    "cast_f32_to_bf16: pointers must be 16-byte aligned");
     cast_f32_to_bf16_kernel<<<grid_for(n / 8 + 1, 256, ctx->num_sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         src, static_cast<__nv_bfloat16*>(dst), n);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200clip_split_f32_to_bf16(b200clip_ctx* ctx, const float* src, void* hi, void* lo, int64_t n,
+                                          void* stream) {
+    B200_CHECK_CTX(ctx);
+    B200_CHECK_ARG(src && hi && lo && n > 0, "split_f32_to_bf16: bad argument");
+    split_f32_to_bf16_kernel<<<grid_for(n, 256, ctx->num_sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        src, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), n);
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -105,24 +105,40 @@ struct EpiOperands {
     // Loads are UNCONDITIONAL from clamped (always valid) addresses so that all eight are in flight
     // at once -- a `cond ? load : 0` select puts a dependent MOV behind every load and serialises
     // them.  Values fetched for out-of-range rows / columns are never stored.
+    // FULL: the whole 32 x 32 block is inside the matrix (warp-uniform), no clamping needed.
+    template <bool FULL>
     __device__ __forceinline__ void load(const GemmParams& p, int m_base, int col0, int lane) {
         const int rrow = lane >> 3;
         int col = col0 + (lane & 7) * 4;
-        col = col < p.N ? col : 0;  // N % 8 == 0 and col % 4 == 0: the 4 columns are all in or all out
+        if constexpr (!FULL) col = col < p.N ? col : 0;  // N % 8 == 0 and col % 4 == 0: the 4 columns are all in or all out
         if constexpr (AUX_F32) {
             const float* ap = reinterpret_cast<const float*>(p.aux) + col;
+            if constexpr (FULL) {
+                ap += static_cast<int64_t>(m_base + rrow) * p.ldaux;
+                const int64_t rs = 4 * p.ldaux;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int grow = min(m_base + 4 * i + rrow, p.M - 1);
-                auxf[i] = *reinterpret_cast<const uint4*>(ap + static_cast<int64_t>(grow) * p.ldaux);
+                for (int i = 0; i < 8; ++i) auxf[i] = *reinterpret_cast<const uint4*>(ap + i * rs);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int grow = min(m_base + 4 * i + rrow, p.M - 1);
+                    auxf[i] = *reinterpret_cast<const uint4*>(ap + static_cast<int64_t>(grow) * p.ldaux);
+                }
             }
         }
         if constexpr (AUX_BF16) {
             const __nv_bfloat16* ap = p.aux + col;
+            if constexpr (FULL) {
+                ap += static_cast<int64_t>(m_base + rrow) * p.ldaux;
+                const int64_t rs = 4 * p.ldaux;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int grow = min(m_base + 4 * i + rrow, p.M - 1);
-                auxh[i] = *reinterpret_cast<const uint2*>(ap + static_cast<int64_t>(grow) * p.ldaux);
+                for (int i = 0; i < 8; ++i) auxh[i] = *reinterpret_cast<const uint2*>(ap + i * rs);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int grow = min(m_base + 4 * i + rrow, p.M - 1);
+                    auxh[i] = *reinterpret_cast<const uint2*>(ap + static_cast<int64_t>(grow) * p.ldaux);
+                }
             }
         }
         b0 = b1 = b2 = b3 = 0.f;
@@ -134,14 +150,18 @@ struct EpiOperands {
     }
 };
 
-template <int EPI, bool OUT_F32, bool ATOMIC>
+// FULL (warp-uniform): all 32 rows and 32 columns of the block are inside the matrix, so the bounds
+// predicates and the branches around the maths disappear; PRE: the pre-activation is stored too.
+// Both are compile-time so that the hot loop is straight-line code (measured: the generic form spent
+// ~15 instructions per element, 6 of them on predicates / pointer selects / re-materialised descriptors).
+template <int EPI, bool OUT_F32, bool ATOMIC, bool FULL, bool PRE>
 __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOperands<EPI, OUT_F32>& op, uint32_t taddr,
                                                int m_base, int col0, float scale, uint8_t* stg, int lane) {
     using Op = EpiOperands<EPI, OUT_F32>;
     using OutT = typename std::conditional<OUT_F32, float, __nv_bfloat16>::type;
     const int rrow = lane >> 3, rch = lane & 7;
     const int col = col0 + rch * 4;
-    const bool col_ok = col < p.N;
+    const bool col_ok = FULL ? true : col < p.N;
     uint32_t acc[32];
     tmem_ld_32x32(taddr, acc);
     tmem_ld_wait();
@@ -154,9 +174,10 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
     // 64-bit multiply); rows_left turns the row bound into a compare against the unrolled index.
     const int64_t first = static_cast<int64_t>(m_base + rrow) * p.ldc + col;
     OutT* cptr = reinterpret_cast<OutT*>(p.C) + first;
-    [[maybe_unused]] __nv_bfloat16* pptr = (EPI == B200CLIP_EPI_QUICKGELU && p.preact != nullptr) ? p.preact + first : nullptr;
+    [[maybe_unused]] __nv_bfloat16* pptr = PRE ? p.preact + first : nullptr;
     const int64_t rstride = 4 * p.ldc;
-    const int rows_left = col_ok ? (p.M - m_base - rrow + 3) >> 2 : 0;  // number of valid i (rows m_base+rrow+4i < M)
+    // number of valid i (rows m_base+rrow+4i < M)
+    [[maybe_unused]] const int rows_left = FULL ? 8 : (col_ok ? (p.M - m_base - rrow + 3) >> 2 : 0);
     [[maybe_unused]] float cs0 = 0.f, cs1 = 0.f, cs2 = 0.f, cs3 = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -164,9 +185,11 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
         const uint4 v = *reinterpret_cast<const uint4*>(stg + stage_off(row, rch));
         float x0 = fmaf(__uint_as_float(v.x), scale, op.b0), x1 = fmaf(__uint_as_float(v.y), scale, op.b1);
         float x2 = fmaf(__uint_as_float(v.z), scale, op.b2), x3 = fmaf(__uint_as_float(v.w), scale, op.b3);
-        const bool ok = i < rows_left;
+        const bool ok = FULL ? true : i < rows_left;
         if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
-            if (pptr != nullptr && ok) *reinterpret_cast<uint2*>(pptr) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+            if constexpr (PRE) {
+                if (ok) *reinterpret_cast<uint2*>(pptr) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
+            }
             x0 = qgelu_fast(x0); x1 = qgelu_fast(x1); x2 = qgelu_fast(x2); x3 = qgelu_fast(x3);
         } else if constexpr (Op::AUX_F32) {
             x0 += __uint_as_float(op.auxf[i].x); x1 += __uint_as_float(op.auxf[i].y);
@@ -194,9 +217,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
             }
         }
         cptr += rstride;
-        if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
-            if (pptr != nullptr) pptr += rstride;
-        }
+        if constexpr (PRE) pptr += rstride;
     }
     if constexpr (EPI == B200CLIP_EPI_QUICKGELU_BWD) {
         if (p.colsum != nullptr) {  // warp-uniform
@@ -209,6 +230,37 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
         }
     }
     __syncwarp();  // the staging tile is rewritten by the next block
+}
+
+// One warp's share of one tile (nblk 32 x 32 blocks), specialised on "entirely inside the matrix"
+// (FULL) and "stores the pre-activation" (PRE).
+template <int EPI, bool OUT_F32, bool ATOMIC, bool FULL, bool PRE>
+__device__ __forceinline__ void drain_tile(const GemmParams& p, uint64_t* full_bar, uint32_t phase, uint32_t taddr,
+                                           int m_base, int n_base, int nblk, float scale, uint8_t* stg, int lane) {
+    EpiOperands<EPI, OUT_F32> opA;
+    if (nblk > 0) opA.template load<FULL>(p, m_base, n_base, lane);  // before waiting for the accumulator
+    mbar_wait(full_bar, phase);
+    __syncwarp();
+    tc_fence_after();
+    if constexpr (!FULL) {  // edge tiles (rare): one operand set, no look-ahead
+#pragma unroll 1
+        for (int j = 0; j < nblk; ++j) {
+            if (j > 0) opA.template load<FULL>(p, m_base, n_base + j * 32, lane);
+            epilogue_block<EPI, OUT_F32, ATOMIC, FULL, PRE>(p, opA, taddr + j * 32, m_base, n_base + j * 32, scale, stg, lane);
+        }
+        return;
+    }
+    EpiOperands<EPI, OUT_F32> opB;  // ping-pong: the next block's operands load while this one runs
+#pragma unroll 1
+    for (int j = 0; j < nblk; j += 2) {
+        if (j + 1 < nblk) opB.template load<FULL>(p, m_base, n_base + (j + 1) * 32, lane);
+        epilogue_block<EPI, OUT_F32, ATOMIC, FULL, PRE>(p, opA, taddr + j * 32, m_base, n_base + j * 32, scale, stg, lane);
+        if (j + 1 < nblk) {
+            if (j + 2 < nblk) opA.template load<FULL>(p, m_base, n_base + (j + 2) * 32, lane);
+            epilogue_block<EPI, OUT_F32, ATOMIC, FULL, PRE>(p, opB, taddr + (j + 1) * 32, m_base, n_base + (j + 1) * 32,
+                                                            scale, stg, lane);
+        }
+    }
 }
 
 // The whole persistent loop of one epilogue warp, specialised on the epilogue flavour.
@@ -233,23 +285,25 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
         int nblk = (BN / 2) >> 5;
         const int valid = (p.N - n_base + 31) >> 5;  // blocks with at least one real column (warp-uniform)
         if (valid < nblk) nblk = valid;
-        EpiOperands<EPI, OUT_F32> opA, opB;  // ping-pong: the next block's operands load while this one runs
-        if (nblk > 0) opA.load(p, m_base, n_base, lane);  // before waiting for the accumulator
-        mbar_wait(&tmem_full_bar[as], aphase);
-        __syncwarp();
-        tc_fence_after();
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                static_cast<uint32_t>(as * BN + half * (BN / 2));
-#pragma unroll 1
-        for (int j = 0; j < nblk; j += 2) {
-            if (j + 1 < nblk) opB.load(p, m_base, n_base + (j + 1) * 32, lane);
-            epilogue_block<EPI, OUT_F32, ATOMIC>(p, opA, taddr + j * 32, m_base, n_base + j * 32, scale, stg, lane);
-            if (j + 1 < nblk) {
-                if (j + 2 < nblk) opA.load(p, m_base, n_base + (j + 2) * 32, lane);
-                epilogue_block<EPI, OUT_F32, ATOMIC>(p, opB, taddr + (j + 1) * 32, m_base, n_base + (j + 1) * 32, scale,
-                                                     stg, lane);
+        const bool full = (m_base + 32 <= p.M) && (n_base + nblk * 32 <= p.N);
+#define B200_DRAIN(FULL, PRE)                                                                                       \
+    drain_tile<EPI, OUT_F32, ATOMIC, FULL, PRE>(p, &tmem_full_bar[as], aphase, taddr, m_base, n_base, nblk, scale, stg, \
+                                                lane)
+        if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
+            if (p.preact != nullptr) {
+                if (full) B200_DRAIN(true, true);
+                else B200_DRAIN(false, true);
+            } else {
+                if (full) B200_DRAIN(true, false);
+                else B200_DRAIN(false, false);
             }
+        } else {
+            if (full) B200_DRAIN(true, false);
+            else B200_DRAIN(false, false);
         }
+#undef B200_DRAIN
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {

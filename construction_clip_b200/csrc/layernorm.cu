@@ -130,106 +130,164 @@ layernorm_fwd_kernel(const TX* __restrict__ x, int64_t ldx, const int32_t* __res
     }
 }
 
+// 4 consecutive elements <-> 4 floats (shared-memory rows: one 8 / 16-byte access per lane, conflict-free)
+template <typename T>
+__device__ __forceinline__ void load4(const T* p, float (&f)[4]) {
+    if constexpr (sizeof(T) == 2) {
+        const uint2 u = *reinterpret_cast<const uint2*>(p);
+        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y);
+        f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+    } else {
+        const float4 a = *reinterpret_cast<const float4*>(p);
+        f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+    }
+}
+
 // dx = dres + rstd * (g - mean(g) - xhat * mean(g*xhat)),  g = dy*gamma,  xhat = (x-mean)*rstd
-// Two passes over the row: pass 1 accumulates the two row reductions and the per-column partial sums
-// of dgamma / dbeta; pass 2 re-reads x, dy (L1 hits: a row is a few KB) and writes dx.  Only the
-// column accumulators live across rows, which keeps the kernel at <= 128 registers and 16 warps / SM.
-template <int NV, typename TX, bool COLSUM>
-__global__ void __launch_bounds__(kLnThreads, (NV <= 3) ? 2 : 1)
+// plus the column sums dgamma = sum dy*xhat, dbeta = sum dy and (optionally) sum dx.
+// One warp per row.  Every warp runs its own two-stage pipeline: lane 0 fetches the NEXT row's x, dy and
+// dres with 1-D bulk copies into the warp's private shared-memory stage (completion on a per-warp
+// mbarrier) while the warp makes its two passes over the CURRENT row out of shared memory, so no DRAM
+// latency is exposed and the only per-thread state is the column accumulators.
+// Lane l owns the 4-column units u = l + 32*m (m < NU): d <= NU * 128.
+template <int NU, typename TX, bool COLSUM>
+__global__ void __launch_bounds__(kLnThreads, (NU <= 6) ? 2 : 1)
 layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const TX* __restrict__ x,
                      int64_t ldx, const int32_t* __restrict__ row_index, const __nv_bfloat16* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      const __nv_bfloat16* __restrict__ dres, int64_t lddres, __nv_bfloat16* __restrict__ dx,
                      int64_t lddx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ dx_colsum, int rows, int d) {
-    extern __shared__ float s_acc[];  // [3][d]
-    const int lane = threadIdx.x & 31;
-    const int warps_per_block = kLnThreads / 32;
-    const int nvec = d >> 3;
-    for (int i = threadIdx.x; i < 3 * d; i += kLnThreads) s_acc[i] = 0.f;
+    extern __shared__ __align__(128) uint8_t s_ln[];  // float acc[3][d] | bf16 gamma[d] | per warp: 2 stages x {x | dy | dres}
+    __shared__ uint64_t s_bar[kLnThreads / 32][2];
+    float* s_acc = reinterpret_cast<float*>(s_ln);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int wpb = blockDim.x >> 5;
+    const int nunit = d >> 2;
+    const uint32_t xb = static_cast<uint32_t>(d) * sizeof(TX), yb = static_cast<uint32_t>(d) * 2u;
+    const uint32_t stage_bytes = xb + 2u * yb;
+    __nv_bfloat16* s_gamma = reinterpret_cast<__nv_bfloat16*>(s_ln + static_cast<size_t>(3) * d * sizeof(float));
+    uint8_t* wbase = s_ln + static_cast<size_t>(3) * d * sizeof(float) + yb + static_cast<size_t>(warp) * 2u * stage_bytes;
+    for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) s_acc[i] = 0.f;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) s_gamma[i] = gamma[i];
+    if (lane == 0) {
+        mbar_init(&s_bar[warp][0], 1);
+        mbar_init(&s_bar[warp][1], 1);
+        fence_barrier_init();
+    }
     __syncthreads();
 
-    float ag[NV][8], ab[NV][8];
-    float ac[COLSUM ? NV : 1][8];
-#pragma unroll
-    for (int i = 0; i < NV; ++i)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            ag[i][j] = ab[i][j] = 0.f;
-            if constexpr (COLSUM) ac[i][j] = 0.f;
-        }
-    for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
+    auto issue = [&](int r, int stage) {  // lane 0
         const int64_t src = row_index ? row_index[r] : r;
-        const float mu = mean[r], rs = rstd[r];
-        const TX* xr = x + src * ldx;
-        const __nv_bfloat16* dyr = dy + static_cast<int64_t>(r) * lddy;
+        uint8_t* sb = wbase + stage * stage_bytes;
+        uint64_t* bar = &s_bar[warp][stage];
+        mbar_arrive_expect_tx(bar, xb + yb + (dres != nullptr ? yb : 0u));
+        bulk_load_1d(sb, x + src * ldx, xb, bar);
+        bulk_load_1d(sb + xb, dy + static_cast<int64_t>(r) * lddy, yb, bar);
+        if (dres != nullptr) bulk_load_1d(sb + xb + yb, dres + static_cast<int64_t>(r) * lddres, yb, bar);
+    };
+
+    float ag[NU][4], ab[NU][4];
+    float ac[COLSUM ? NU : 1][4];
+#pragma unroll
+    for (int m = 0; m < NU; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            ag[m][j] = ab[m][j] = 0.f;
+            if constexpr (COLSUM) ac[m][j] = 0.f;
+        }
+    const int stride = gridDim.x * wpb;
+    int r = blockIdx.x * wpb + warp;
+    float mu_n = 0.f, rs_n = 0.f;
+    if (r < rows) {
+        if (lane == 0) issue(r, 0);
+        mu_n = mean[r];
+        rs_n = rstd[r];
+    }
+    const float inv_d = 1.0f / d;
+    for (uint32_t k = 0; r < rows; r += stride, ++k) {
+        const uint32_t st = k & 1u;
+        const float mu = mu_n, rs = rs_n;
+        const int rn = r + stride;
+        __syncwarp();  // every lane is done with the other stage (read during the previous row)
+        if (rn < rows) {
+            if (lane == 0) issue(rn, st ^ 1u);
+            mu_n = mean[rn];
+            rs_n = rstd[rn];
+        }
+        mbar_wait(&s_bar[warp][st], (k >> 1) & 1u);
+        const uint8_t* sb = wbase + st * stage_bytes;
+        const TX* xr = reinterpret_cast<const TX*>(sb);
+        const __nv_bfloat16* dyr = reinterpret_cast<const __nv_bfloat16*>(sb + xb);
+        const __nv_bfloat16* drr = reinterpret_cast<const __nv_bfloat16*>(sb + xb + yb);
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int vec = lane + 32 * i;
-            if (vec < nvec) {
-                float xf[8], df[8], gf[8];
-                load8(xr + vec * 8, xf);
-                load8(dyr + vec * 8, df);
-                load8(gamma + vec * 8, gf);
+        for (int m = 0; m < NU; ++m) {
+            const int u = lane + 32 * m;
+            if (u < nunit) {
+                float xf[4], df[4], gf[4];
+                load4(xr + u * 4, xf);
+                load4(dyr + u * 4, df);
+                load4(s_gamma + u * 4, gf);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     const float xh = (xf[j] - mu) * rs;
                     const float g = df[j] * gf[j];
-                    ab[i][j] += df[j];
-                    ag[i][j] = fmaf(df[j], xh, ag[i][j]);
+                    ab[m][j] += df[j];
+                    ag[m][j] = fmaf(df[j], xh, ag[m][j]);
                     s1 += g;
                     s2 = fmaf(g, xh, s2);
                 }
             }
         }
-        s1 = warp_sum(s1) / d;
-        s2 = warp_sum(s2) / d;
+        s1 = warp_sum(s1) * inv_d;
+        s2 = warp_sum(s2) * inv_d;
+        const int64_t src = row_index ? row_index[r] : r;
         __nv_bfloat16* dxr = dx + src * lddx;
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int vec = lane + 32 * i;
-            if (vec < nvec) {
-                float xf[8], df[8], gf[8], o[8];
-                load8(xr + vec * 8, xf);
-                load8(dyr + vec * 8, df);
-                load8(gamma + vec * 8, gf);
+        for (int m = 0; m < NU; ++m) {
+            const int u = lane + 32 * m;
+            if (u < nunit) {
+                float xf[4], df[4], gf[4], o[4];
+                load4(xr + u * 4, xf);
+                load4(dyr + u * 4, df);
+                load4(s_gamma + u * 4, gf);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     const float xh = (xf[j] - mu) * rs;
                     o[j] = rs * (df[j] * gf[j] - s1 - xh * s2);
                 }
                 if (dres != nullptr) {
-                    float rf[8];
-                    load8(dres + static_cast<int64_t>(r) * lddres + vec * 8, rf);
+                    float rf[4];
+                    load4(drr + u * 4, rf);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) o[j] += rf[j];
+                    for (int j = 0; j < 4; ++j) o[j] += rf[j];
                 }
-                store8(dxr + vec * 8, o);
+                *reinterpret_cast<uint2*>(dxr + u * 4) = make_uint2(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]));
                 if constexpr (COLSUM) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) ac[i][j] += o[j];
+                    for (int j = 0; j < 4; ++j) ac[m][j] += o[j];
                 }
             }
         }
     }
     if (dgamma != nullptr || COLSUM) {
 #pragma unroll
-        for (int i = 0; i < NV; ++i) {
-            const int vec = lane + 32 * i;
-            if (vec < nvec) {
+        for (int m = 0; m < NU; ++m) {
+            const int u = lane + 32 * m;
+            if (u < nunit) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     if (dgamma != nullptr) {
-                        atomicAdd(&s_acc[vec * 8 + j], ag[i][j]);
-                        atomicAdd(&s_acc[d + vec * 8 + j], ab[i][j]);
+                        atomicAdd(&s_acc[u * 4 + j], ag[m][j]);
+                        atomicAdd(&s_acc[d + u * 4 + j], ab[m][j]);
                     }
-                    if constexpr (COLSUM) atomicAdd(&s_acc[2 * d + vec * 8 + j], ac[i][j]);
+                    if constexpr (COLSUM) atomicAdd(&s_acc[2 * d + u * 4 + j], ac[m][j]);
                 }
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < d; i += kLnThreads) {
+        for (int i = threadIdx.x; i < d; i += blockDim.x) {
             if (dgamma != nullptr) {
                 atomicAdd(&dgamma[i], s_acc[i]);
                 atomicAdd(&dbeta[i], s_acc[d + i]);
@@ -237,6 +295,25 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const T
             if constexpr (COLSUM) atomicAdd(&dx_colsum[i], s_acc[2 * d + i]);
         }
     }
+}
+
+template <int NU, typename TX, bool COLSUM>
+static cudaError_t launch_ln_bwd(int grid, int threads, size_t smem, cudaStream_t st, const __nv_bfloat16* dy,
+                                 int64_t lddy, const TX* x, int64_t ldx, const int32_t* row_index,
+                                 const __nv_bfloat16* gamma, const float* mean, const float* rstd,
+                                 const __nv_bfloat16* dres, int64_t lddres, __nv_bfloat16* dx, int64_t lddx,
+                                 float* dgamma, float* dbeta, float* dx_colsum, int rows, int d) {
+    static size_t configured = 0;  // per instantiation; the opt-in only ever grows
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel<NU, TX, COLSUM>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        if (e != cudaSuccess) return e;
+        configured = smem;
+    }
+    layernorm_bwd_kernel<NU, TX, COLSUM><<<grid, threads, smem, st>>>(dy, lddy, x, ldx, row_index, gamma, mean, rstd,
+                                                                       dres, lddres, dx, lddx, dgamma, dbeta, dx_colsum,
+                                                                       rows, d);
+    return cudaSuccess;
 }
 
 }  // namespace b200
@@ -307,30 +384,47 @@ extern "C" int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t
     B200_CHECK_ARG(d >= 8 && d <= 2048 && d % 8 == 0, "layernorm_bwd: bad d=%lld", (long long)d);
     B200_CHECK_ARG(lddy % 8 == 0 && ldx % 8 == 0 && lddx % 8 == 0 && (dres == nullptr || lddres % 8 == 0),
                    "layernorm_bwd: row pitches must be multiples of 8");
-    const int wpb = kLnThreads / 32;
-    const int64_t want = ceil_div(rows, wpb * 4);  // >= 4 rows per warp amortise the dgamma/dbeta atomics
-    const int per_sm = d <= 768 ? 2 : 1;
-    const int grid = static_cast<int>(want < ctx->num_sms * per_sm ? (want > 0 ? want : 1) : ctx->num_sms * per_sm);
-    const size_t smem = 3 * d * sizeof(float);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    B200_CHECK_ARG(((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx) |
+                     reinterpret_cast<uintptr_t>(dres) | reinterpret_cast<uintptr_t>(gamma)) & 15) == 0,
+                   "layernorm_bwd: pointers must be 16-byte aligned");
     B200_CHECK_ARG(x_dtype == B200CLIP_DT_BF16 || x_dtype == B200CLIP_DT_F32, "layernorm_bwd: bad x dtype");
-#define CALL_T(NV, TX, CS)                                                                                          \
-    layernorm_bwd_kernel<NV, TX, CS><<<grid, kLnThreads, smem, st>>>(                                               \
-        static_cast<const __nv_bfloat16*>(dy), lddy, static_cast<const TX*>(x), ldx, row_index,                    \
-        static_cast<const __nv_bfloat16*>(gamma), mean, rstd, static_cast<const __nv_bfloat16*>(dres), lddres,     \
-        static_cast<__nv_bfloat16*>(dx), lddx, dgamma, dbeta, dx_colsum, static_cast<int>(rows), static_cast<int>(d))
-#define CALL(NV)                                                       \
+    // shared memory: 3 column accumulators, gamma, and per warp two stages of {x row, dy row, dres row}
+    const size_t xsz = x_dtype == B200CLIP_DT_F32 ? 4 : 2;
+    const size_t stage = static_cast<size_t>(d) * (xsz + 4);
+    const size_t fixed = static_cast<size_t>(d) * (3 * sizeof(float) + 2);
+    int wpb = kLnThreads / 32;
+    while (wpb > 1 && fixed + wpb * 2 * stage > 200 * 1024) wpb >>= 1;
+    const size_t smem = fixed + wpb * 2 * stage;
+    const int per_sm = (d <= 768 && 2 * (smem + 1024) <= 227 * 1024) ? 2 : 1;
+    const int64_t want = ceil_div(rows, wpb * 4);  // >= 4 rows per warp amortise the dgamma/dbeta atomics
+    const int grid = static_cast<int>(want < ctx->num_sms * per_sm ? (want > 0 ? want : 1) : ctx->num_sms * per_sm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t le = cudaSuccess;
+#define CALL_T(NU, TX, CS)                                                                                         \
+    le = launch_ln_bwd<NU, TX, CS>(grid, wpb * 32, smem, st, static_cast<const __nv_bfloat16*>(dy), lddy,          \
+                                   static_cast<const TX*>(x), ldx, row_index,                                      \
+                                   static_cast<const __nv_bfloat16*>(gamma), mean, rstd,                           \
+                                   static_cast<const __nv_bfloat16*>(dres), lddres, static_cast<__nv_bfloat16*>(dx), \
+                                   lddx, dgamma, dbeta, dx_colsum, static_cast<int>(rows), static_cast<int>(d))
+#define CALL(NU)                                                       \
     do {                                                               \
         if (x_dtype == B200CLIP_DT_BF16) {                             \
-            if (dx_colsum) { CALL_T(NV, __nv_bfloat16, true); }        \
-            else { CALL_T(NV, __nv_bfloat16, false); }                 \
+            if (dx_colsum) { CALL_T(NU, __nv_bfloat16, true); }        \
+            else { CALL_T(NU, __nv_bfloat16, false); }                 \
         } else {                                                       \
-            if (dx_colsum) { CALL_T(NV, float, true); }                \
-            else { CALL_T(NV, float, false); }                         \
+            if (dx_colsum) { CALL_T(NU, float, true); }                \
+            else { CALL_T(NU, float, false); }                         \
         }                                                              \
     } while (0)
-    LN_DISPATCH(d, CALL);
+    if (d <= 256) { CALL(2); }
+    else if (d <= 512) { CALL(4); }
+    else if (d <= 768) { CALL(6); }
+    else if (d <= 1024) { CALL(8); }
+    else if (d <= 1536) { CALL(12); }
+    else { CALL(16); }
 #undef CALL
+#undef CALL_T
+    B200_CHECK_CUDA(le);
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -40,6 +40,7 @@ SIGNATURES = {
     "b200clip_l2norm_fwd": [_p, _p, _p, _p, _l, _l, _p],
     "b200clip_l2norm_bwd": [_p, _p, _p, _p, _p, _l, _l, _p],
     "b200clip_cast_f32_to_bf16": [_p, _p, _p, _l, _p],
+    "b200clip_split_f32_to_bf16": [_p, _p, _p, _p, _l, _p],
     "b200clip_cast_bf16_to_f32": [_p, _p, _p, _l, _p],
     "b200clip_logits": [_p, _p, _p, _p, _p, _l, _l, _l, _p],
     "b200clip_clip_loss_workspace_bytes": [_p, _l, _l, _l],

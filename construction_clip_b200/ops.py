@@ -241,6 +241,17 @@ def cast_f32_to_bf16(src, dst=None):
     return dst
 
 
+def split_f32_to_bf16(src):
+    """(hi, lo) bf16 pair with hi + lo ~= src to ~16 mantissa bits."""
+    src = src.contiguous()
+    hi = torch.empty(src.shape, device=src.device, dtype=bf16)
+    lo = torch.empty(src.shape, device=src.device, dtype=bf16)
+    ctx, st = _ctx_stream(src)
+    L.check(L.load().b200clip_split_f32_to_bf16(ctx, src.data_ptr(), hi.data_ptr(), lo.data_ptr(), src.numel(), st),
+            "split_f32_to_bf16")
+    return hi, lo
+
+
 def logits(img_n, txt_n, logit_scale):
     Bi, E = img_n.shape
     Bt = txt_n.shape[0]

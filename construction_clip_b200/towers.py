@@ -119,10 +119,14 @@ def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved):
 def _pool_project_fwd(W, x, row_index, ln_w, ln_b, proj, save):
     """ln(x[row_index]) @ proj -> fp32 [B, E]   (visual.ln_post + visual.proj / ln_final + text_projection)."""
     if save:
-        pooled, mean, rstd = O.layernorm_fwd(x, W[ln_w], W[ln_b], row_index=row_index, want_stats=True)
+        pooled32, mean, rstd = O.layernorm_fwd(x, W[ln_w], W[ln_b], row_index=row_index, want_stats=True, out_dtype=f32)
     else:
-        pooled, mean, rstd = O.layernorm_fwd(x, W[ln_w], W[ln_b], row_index=row_index), None, None
+        pooled32, mean, rstd = O.layernorm_fwd(x, W[ln_w], W[ln_b], row_index=row_index, out_dtype=f32), None, None
+    # The projection input is only B rows, but rounding it to bf16 is the single largest term of the
+    # logit error (100 * 2^-9 / sqrt(E) per feature): feed it as a hi + lo bf16 pair instead.
+    pooled, lo = O.split_f32_to_bf16(pooled32)
     feat = O.gemm(pooled, W[proj], b_major=L.MAJOR_MN, out_dtype=f32)  # proj stored [d, E]
+    O.gemm(lo, W[proj], b_major=L.MAJOR_MN, out=feat, accumulate=True)
     return feat, (pooled, mean, rstd)
 
 

@@ -165,6 +165,10 @@ int b200clip_l2norm_bwd(b200clip_ctx* ctx, const float* dy, const float* y, cons
                         int64_t B, int64_t E, void* stream);
 /* dtype conversion of flat buffers (n elements) */
 int b200clip_cast_f32_to_bf16(b200clip_ctx* ctx, const float* src, void* dst, int64_t n, void* stream);
+/* hi = bf16(src), lo = bf16(src - hi): lets a bf16 GEMM consume an fp32 operand at ~16 mantissa bits
+ * (C = hi.W, then C += lo.W).  Used for the final feature projection (clip/model.py: `x @ self.proj`,
+ * `x @ self.text_projection`), whose input rounding would otherwise dominate the logit error. */
+int b200clip_split_f32_to_bf16(b200clip_ctx* ctx, const float* src, void* hi, void* lo, int64_t n, void* stream);
 int b200clip_cast_bf16_to_f32(b200clip_ctx* ctx, const void* src, float* dst, int64_t n, void* stream);
 
 /* ---- logit_scale.exp() * I @ T.t()  (CLIP.forward) ---------------------------------------------
