@@ -24,6 +24,24 @@ namespace b200 {
 constexpr int BM = 128;           // tile rows  (UMMA M, cta_group::1)
 constexpr int BK = 64;            // k-block: 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;        // fixed for 16-bit inputs
+// Epilogue scheduling knobs (compile-time; tools/build_variants.py builds A/B variants of the library).
+// Same-box A/B over the 24 GEMM shapes of a ViT-B/32 layer (per-layer total, us; 3495 before any of them):
+//   all off (only the per-tile bias fetch)            3449   <- default
+//   LDTM look-ahead + early release                   3487
+//   full-tile straight-line path                      3553
+//   full-tile path + look-ahead + early release       3530
+// The straight-line path halves the instruction count but bursts its 8 row stores; the predicated
+// per-row form spreads them and is faster -- the epilogue is bound by the latency of its global
+// accesses (8 warps issue all of an SM's output traffic), not by issue slots.
+#ifndef B200_EPI_LDTM_AHEAD
+#define B200_EPI_LDTM_AHEAD 0   // issue block j+1's TMEM load as soon as block j is staged
+#endif
+#ifndef B200_EPI_FULL_SPEC
+#define B200_EPI_FULL_SPEC 0    // straight-line code path for tiles entirely inside the matrix
+#endif
+#ifndef B200_EPI_EARLY_RELEASE
+#define B200_EPI_EARLY_RELEASE 0  // hand the TMEM stage back after the last TMEM load, not the last store
+#endif
 constexpr int kEpiWarps = 8;       // two warps per TMEM lane quadrant, each takes half of the tile's columns
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kStageBytesA = BM * BK * 2;  // 16 KB
@@ -91,16 +109,15 @@ __device__ __forceinline__ float qgelu_bwd_fast(float acc, float x) {
     return fmaf(h, c, h);
 }
 
-// per-lane operands of one 32x32 block that do not depend on the accumulator: aux (coalesced layout:
-// 8 rows x 4 columns) and bias (4 columns).  Fetched one block ahead so that global-memory latency
-// is off the critical path (the first block of a tile is fetched before waiting for the MMA).
+// per-lane aux operands of one 32x32 block (coalesced layout: 8 rows x 4 columns).  Fetched one block
+// ahead so that global-memory latency is off the critical path (the first block of a tile is fetched
+// before waiting for the MMA).  The bias of ALL the tile's blocks is fetched once per tile (drain_tile).
 template <int EPI, bool OUT_F32>
 struct EpiOperands {
     static constexpr bool AUX_F32 = (EPI == B200CLIP_EPI_RESIDUAL) && OUT_F32;
     static constexpr bool AUX_BF16 = (EPI == B200CLIP_EPI_QUICKGELU_BWD) || (EPI == B200CLIP_EPI_RESIDUAL && !OUT_F32);
     uint4 auxf[AUX_F32 ? 8 : 1];
     uint2 auxh[AUX_BF16 ? 8 : 1];
-    float b0, b1, b2, b3;
 
     // Loads are UNCONDITIONAL from clamped (always valid) addresses so that all eight are in flight
     // at once -- a `cond ? load : 0` select puts a dependent MOV behind every load and serialises
@@ -141,12 +158,6 @@ struct EpiOperands {
                 }
             }
         }
-        b0 = b1 = b2 = b3 = 0.f;
-        if (p.bias != nullptr) {
-            const uint2 bb = __ldg(reinterpret_cast<const uint2*>(p.bias + col));
-            const float2 f0 = unpack_bf16(bb.x), f1 = unpack_bf16(bb.y);
-            b0 = f0.x; b1 = f0.y; b2 = f1.x; b3 = f1.y;
-        }
     }
 };
 
@@ -154,22 +165,42 @@ struct EpiOperands {
 // predicates and the branches around the maths disappear; PRE: the pre-activation is stored too.
 // Both are compile-time so that the hot loop is straight-line code (measured: the generic form spent
 // ~15 instructions per element, 6 of them on predicates / pointer selects / re-materialised descriptors).
-template <int EPI, bool OUT_F32, bool ATOMIC, bool FULL, bool PRE>
-__device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOperands<EPI, OUT_F32>& op, uint32_t taddr,
-                                               int m_base, int col0, float scale, uint8_t* stg, int lane) {
+template <int EPI, bool OUT_F32, bool ATOMIC, bool FULL, bool PRE, bool PAIR>
+__device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOperands<EPI, OUT_F32>& op, uint2 bias_pk,
+                                               uint32_t (&acc)[32], uint32_t taddr_cur, uint32_t taddr_next,
+                                               uint64_t* release_bar, int m_base, int col0, float scale, uint8_t* stg,
+                                               int lane) {
     using Op = EpiOperands<EPI, OUT_F32>;
     using OutT = typename std::conditional<OUT_F32, float, __nv_bfloat16>::type;
     const int rrow = lane >> 3, rch = lane & 7;
     const int col = col0 + rch * 4;
     const bool col_ok = FULL ? true : col < p.N;
-    uint32_t acc[32];
-    tmem_ld_32x32(taddr, acc);
-    tmem_ld_wait();
+    const float2 bf0 = unpack_bf16(bias_pk.x), bf1 = unpack_bf16(bias_pk.y);
+#if !B200_EPI_LDTM_AHEAD
+    tmem_ld_32x32(taddr_cur, acc);
+#endif
+    tmem_ld_wait();  // (look-ahead: this block's accumulator load was issued during the previous block)
+    tc_fence_before();
     // ---- transpose: row layout -> staging
 #pragma unroll
     for (int c = 0; c < 8; ++c)
         *reinterpret_cast<uint4*>(stg + stage_off(lane, c)) = make_uint4(acc[4 * c], acc[4 * c + 1], acc[4 * c + 2], acc[4 * c + 3]);
     __syncwarp();
+    // the accumulator registers are free again: fetch the next block under this block's maths, or, after
+    // the tile's last block, hand the TMEM stage back to the MMA warp right away
+    if (taddr_next != 0u) {
+#if B200_EPI_LDTM_AHEAD
+        tmem_ld_32x32(taddr_next, acc);
+#endif
+    }
+#if B200_EPI_EARLY_RELEASE
+    else if (lane == 0) {  // every lane's loads completed before the __syncwarp above
+        if constexpr (PAIR)
+            mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), 0));  // the leader's barrier
+        else
+            mbar_arrive(release_bar);
+    }
+#endif
     // ---- coalesced layout: maths + stores.  Row pointers advance by a constant stride (no per-row
     // 64-bit multiply); rows_left turns the row bound into a compare against the unrolled index.
     const int64_t first = static_cast<int64_t>(m_base + rrow) * p.ldc + col;
@@ -183,8 +214,8 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
     for (int i = 0; i < 8; ++i) {
         const int row = 4 * i + rrow;
         const uint4 v = *reinterpret_cast<const uint4*>(stg + stage_off(row, rch));
-        float x0 = fmaf(__uint_as_float(v.x), scale, op.b0), x1 = fmaf(__uint_as_float(v.y), scale, op.b1);
-        float x2 = fmaf(__uint_as_float(v.z), scale, op.b2), x3 = fmaf(__uint_as_float(v.w), scale, op.b3);
+        float x0 = fmaf(__uint_as_float(v.x), scale, bf0.x), x1 = fmaf(__uint_as_float(v.y), scale, bf0.y);
+        float x2 = fmaf(__uint_as_float(v.z), scale, bf1.x), x3 = fmaf(__uint_as_float(v.w), scale, bf1.y);
         const bool ok = FULL ? true : i < rows_left;
         if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
             if constexpr (PRE) {
@@ -230,37 +261,83 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
         }
     }
     __syncwarp();  // the staging tile is rewritten by the next block
+#if !B200_EPI_EARLY_RELEASE
+    if (taddr_next == 0u && lane == 0) {
+        if constexpr (PAIR)
+            mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), 0));
+        else
+            mbar_arrive(release_bar);
+    }
+#endif
 }
 
-// One warp's share of one tile (nblk 32 x 32 blocks), specialised on "entirely inside the matrix"
-// (FULL) and "stores the pre-activation" (PRE).
-template <int EPI, bool OUT_F32, bool ATOMIC, bool FULL, bool PRE>
-__device__ __forceinline__ void drain_tile(const GemmParams& p, uint64_t* full_bar, uint32_t phase, uint32_t taddr,
-                                           int m_base, int n_base, int nblk, float scale, uint8_t* stg, int lane) {
+// One warp's share of one tile (nblk <= 4 blocks of 32 x 32), specialised on "entirely inside the
+// matrix" (FULL) and "stores the pre-activation" (PRE).  Per-block latencies are taken off the
+// critical path: the bias of every block is fetched before the accumulator is even complete, aux
+// operands one block ahead, the TMEM load of block j+1 is issued as soon as block j is staged, and
+// the TMEM stage is released right after the last TMEM load instead of after the last store.
+template <int EPI, bool OUT_F32, bool ATOMIC, bool FULL, bool PRE, bool PAIR>
+__device__ __forceinline__ void drain_tile(const GemmParams& p, uint64_t* full_bar, uint32_t phase,
+                                           uint64_t* release_bar, uint32_t taddr, int m_base, int n_base, int nblk,
+                                           float scale, uint8_t* stg, int lane) {
+    uint2 bias_pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        bias_pk[j] = make_uint2(0u, 0u);
+        if (p.bias != nullptr && j < nblk) {
+            int col = n_base + j * 32 + (lane & 7) * 4;
+            if constexpr (!FULL) col = col < p.N ? col : 0;
+            bias_pk[j] = __ldg(reinterpret_cast<const uint2*>(p.bias + col));
+        }
+    }
     EpiOperands<EPI, OUT_F32> opA;
     if (nblk > 0) opA.template load<FULL>(p, m_base, n_base, lane);  // before waiting for the accumulator
     mbar_wait(full_bar, phase);
     __syncwarp();
     tc_fence_after();
-    if constexpr (!FULL) {  // edge tiles (rare): one operand set, no look-ahead
-#pragma unroll 1
-        for (int j = 0; j < nblk; ++j) {
-            if (j > 0) opA.template load<FULL>(p, m_base, n_base + j * 32, lane);
-            epilogue_block<EPI, OUT_F32, ATOMIC, FULL, PRE>(p, opA, taddr + j * 32, m_base, n_base + j * 32, scale, stg, lane);
+    uint32_t acc[32];
+    if (nblk > 0) {
+#if B200_EPI_LDTM_AHEAD
+        tmem_ld_32x32(taddr, acc);
+#endif
+    } else {  // nothing to drain (tile entirely past N): just hand the stage back
+        tc_fence_before();
+        if (lane == 0) {
+            if constexpr (PAIR)
+                mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), 0));
+            else
+                mbar_arrive(release_bar);
+        }
+        return;
+    }
+#define B200_NEXT(j) taddr + (j) * 32, ((j) + 1 < nblk ? taddr + ((j) + 1) * 32 : 0u)
+    if constexpr (!FULL && B200_EPI_FULL_SPEC) {  // edge tiles (rare): one operand set, no look-ahead
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            if (j < nblk) {
+                if (j > 0) opA.template load<FULL>(p, m_base, n_base + j * 32, lane);
+                epilogue_block<EPI, OUT_F32, ATOMIC, FULL, PRE, PAIR>(p, opA, bias_pk[j], acc, B200_NEXT(j), release_bar,
+                                                                      m_base, n_base + j * 32, scale, stg, lane);
+            }
         }
         return;
     }
     EpiOperands<EPI, OUT_F32> opB;  // ping-pong: the next block's operands load while this one runs
-#pragma unroll 1
-    for (int j = 0; j < nblk; j += 2) {
-        if (j + 1 < nblk) opB.template load<FULL>(p, m_base, n_base + (j + 1) * 32, lane);
-        epilogue_block<EPI, OUT_F32, ATOMIC, FULL, PRE>(p, opA, taddr + j * 32, m_base, n_base + j * 32, scale, stg, lane);
-        if (j + 1 < nblk) {
-            if (j + 2 < nblk) opA.template load<FULL>(p, m_base, n_base + (j + 2) * 32, lane);
-            epilogue_block<EPI, OUT_F32, ATOMIC, FULL, PRE>(p, opB, taddr + (j + 1) * 32, m_base, n_base + (j + 1) * 32,
-                                                            scale, stg, lane);
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+        if (j < nblk) {
+            if (j + 1 < nblk) opB.template load<FULL>(p, m_base, n_base + (j + 1) * 32, lane);
+            epilogue_block<EPI, OUT_F32, ATOMIC, FULL, PRE, PAIR>(p, opA, bias_pk[j], acc, B200_NEXT(j), release_bar, m_base,
+                                                                  n_base + j * 32, scale, stg, lane);
+            if (j + 1 < nblk) {
+                if (j + 2 < nblk) opA.template load<FULL>(p, m_base, n_base + (j + 2) * 32, lane);
+                epilogue_block<EPI, OUT_F32, ATOMIC, FULL, PRE, PAIR>(p, opB, bias_pk[j + 1], acc, B200_NEXT(j + 1),
+                                                                      release_bar, m_base, n_base + (j + 1) * 32, scale,
+                                                                      stg, lane);
+            }
         }
     }
+#undef B200_NEXT
 }
 
 // The whole persistent loop of one epilogue warp, specialised on the epilogue flavour.
@@ -287,10 +364,10 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
         if (valid < nblk) nblk = valid;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
                                static_cast<uint32_t>(as * BN + half * (BN / 2));
-        const bool full = (m_base + 32 <= p.M) && (n_base + nblk * 32 <= p.N);
-#define B200_DRAIN(FULL, PRE)                                                                                       \
-    drain_tile<EPI, OUT_F32, ATOMIC, FULL, PRE>(p, &tmem_full_bar[as], aphase, taddr, m_base, n_base, nblk, scale, stg, \
-                                                lane)
+        const bool full = B200_EPI_FULL_SPEC && (m_base + 32 <= p.M) && (n_base + nblk * 32 <= p.N);
+#define B200_DRAIN(FULL, PRE)                                                                                      \
+    drain_tile<EPI, OUT_F32, ATOMIC, FULL, PRE, PAIR>(p, &tmem_full_bar[as], aphase, &tmem_empty_bar[as], taddr, m_base, \
+                                                      n_base, nblk, scale, stg, lane)
         if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
             if (p.preact != nullptr) {
                 if (full) B200_DRAIN(true, true);
@@ -304,14 +381,6 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
             else B200_DRAIN(false, false);
         }
 #undef B200_DRAIN
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) {
-            if constexpr (PAIR)
-                mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[as]), 0));  // the leader's barrier
-            else
-                mbar_arrive(&tmem_empty_bar[as]);
-        }
         if (++as == 2) {
             as = 0;
             aphase ^= 1u;

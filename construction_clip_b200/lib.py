@@ -5,6 +5,8 @@ present, the calls raise ``RuntimeError``.
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 import threading
 from pathlib import Path
@@ -65,11 +67,13 @@ def load() -> C.CDLL:
         return _lib
     with _lock:
         if _lib is None:
-            if not LIB_PATH.exists():
+            # B200CLIP_LIB: an alternative build of the same library (kernel A/B experiments, tools/build_variants.py)
+            path = Path(os.environ["B200CLIP_LIB"]).resolve() if os.environ.get("B200CLIP_LIB") else LIB_PATH
+            if not path.exists():
                 raise RuntimeError(
-                    f"{LIB_PATH} is missing: build it with `python -m construction_clip_b200.build` "
+                    f"{path} is missing: build it with `python -m construction_clip_b200.build` "
                     "(or __graft_entry__.build()).  There is no CPU / PyTorch fallback for the CLIP hot path.")
-            lib = C.CDLL(str(LIB_PATH))
+            lib = C.CDLL(str(path))
             for name, argtypes in SIGNATURES.items():
                 fn = getattr(lib, name)  # AttributeError if the symbol is not exported
                 fn.argtypes = argtypes
