@@ -96,6 +96,11 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
                  "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// L2 prefetch of the 128-byte line holding a global address (LSU path; the bulk / TMA prefetch form
+// competes with the operand loads of a GEMM mainloop for the TMA unit and was measured slower)
+__device__ __forceinline__ void prefetch_l2_line(const void* gsrc) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<uint64_t>(gsrc)) : "memory");
+}
 // L2 prefetch of a tile (no shared memory, no barrier): pulls the box from DRAM into L2 ahead of the
 // real load, so that the load's issue-to-landing latency is the L2 latency
 __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int c0, int c1) {

@@ -39,6 +39,9 @@ constexpr int UMMA_K = 16;        // fixed for 16-bit inputs
 #ifndef B200_EPI_FULL_SPEC
 #define B200_EPI_FULL_SPEC 0    // straight-line code path for tiles entirely inside the matrix
 #endif
+#ifndef B200_EPI_AUX_PREFETCH
+#define B200_EPI_AUX_PREFETCH 1   // L2-prefetch the next tile's aux (residual / pre-activation) rows
+#endif
 #ifndef B200_EPI_EARLY_RELEASE
 #define B200_EPI_EARLY_RELEASE 0  // hand the TMEM stage back after the last TMEM load, not the last store
 #endif
@@ -100,6 +103,15 @@ __device__ __forceinline__ float qgelu_fast(float x) {
 }
 // acc * d/dx[x sigmoid(1.702x)] = 0.5 acc (1 + t + u (1 - t^2)), u = 0.851 x, t = tanh(u)   (6 instr.)
 __device__ __forceinline__ float qgelu_bwd_fast(float acc, float x) {
+#ifdef B200_QGELU_BWD_EX2  // s = sigmoid(1.702 x) by ex2 + rcp:  acc * s * (1 + 1.702 x (1 - s))
+    float e, sg;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.4554669595930157f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.0f + e));
+    const float t1 = 1.702f * x;
+    const float w = fmaf(-t1, sg, t1);  // 1.702 x (1 - s)
+    const float as = acc * sg;
+    return fmaf(as, w, as);
+#endif
     const float u = 0.851f * x;
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
@@ -181,6 +193,16 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
 #endif
     tmem_ld_wait();  // (look-ahead: this block's accumulator load was issued during the previous block)
     tc_fence_before();
+#if defined(B200_EPI_DRY) && B200_EPI_DRY == 1  // measurement only: drain TMEM and drop the block
+    __syncwarp();
+    if (taddr_next == 0u && lane == 0) {
+        if constexpr (PAIR)
+            mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), 0));
+        else
+            mbar_arrive(release_bar);
+    }
+    return;
+#endif
     // ---- transpose: row layout -> staging
 #pragma unroll
     for (int c = 0; c < 8; ++c)
@@ -214,9 +236,17 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
     for (int i = 0; i < 8; ++i) {
         const int row = 4 * i + rrow;
         const uint4 v = *reinterpret_cast<const uint4*>(stg + stage_off(row, rch));
+#if defined(B200_EPI_DRY) && B200_EPI_DRY == 2  // measurement only: staging round trip, no maths / global stores
+        if (p.M < 0) *reinterpret_cast<uint4*>(cptr) = v;
+        continue;
+#endif
         float x0 = fmaf(__uint_as_float(v.x), scale, bf0.x), x1 = fmaf(__uint_as_float(v.y), scale, bf0.y);
         float x2 = fmaf(__uint_as_float(v.z), scale, bf1.x), x3 = fmaf(__uint_as_float(v.w), scale, bf1.y);
+#if defined(B200_EPI_DRY) && B200_EPI_DRY == 3  // measurement only: everything but the global stores
+        const bool ok = (i < rows_left) && (p.M < 0);
+#else
         const bool ok = FULL ? true : i < rows_left;
+#endif
         if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
             if constexpr (PRE) {
                 if (ok) *reinterpret_cast<uint2*>(pptr) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
@@ -257,7 +287,11 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
             cs2 += __shfl_xor_sync(0xffffffffu, cs2, 8);  cs3 += __shfl_xor_sync(0xffffffffu, cs3, 8);
             cs0 += __shfl_xor_sync(0xffffffffu, cs0, 16); cs1 += __shfl_xor_sync(0xffffffffu, cs1, 16);
             cs2 += __shfl_xor_sync(0xffffffffu, cs2, 16); cs3 += __shfl_xor_sync(0xffffffffu, cs3, 16);
+#ifdef B200_EPI_NO_COLSUM_RED  // measurement only
+            if (lane < 8 && col_ok && p.M < 0) red_add_v4(p.colsum + col, cs0, cs1, cs2, cs3);
+#else
             if (lane < 8 && col_ok) red_add_v4(p.colsum + col, cs0, cs1, cs2, cs3);
+#endif
         }
     }
     __syncwarp();  // the staging tile is rewritten by the next block
@@ -355,7 +389,33 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
     const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
     const int w0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
     const int wstep = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    // The pre-activation operand of the QuickGELU' epilogue is streamed once with one block of look-ahead
+    // (2 KB in flight per warp).  Each lane pulls its row of the NEXT tile's aux region into L2 one tile
+    // ahead (plain prefetch.global.L2: -4 % on the two c_proj dgrad shapes).  Not for the fp32 residual
+    // operand (measured +4 % there), and never with the bulk / TMA prefetch form (it queues behind the
+    // mainloop's operand loads: up to 2.4x slower).
+    constexpr bool kHasAux = (EPI == B200CLIP_EPI_QUICKGELU_BWD);
+    constexpr int kAuxElem = (EPI == B200CLIP_EPI_RESIDUAL && OUT_F32) ? 4 : 2;
+    auto prefetch_aux = [&](int wq) {
+        if constexpr (kHasAux && B200_EPI_AUX_PREFETCH) {
+            if (wq < num_work) {
+                const int tq = wq / p.split_k;
+                const int row = (tq / p.num_n_tiles) * (PAIR ? 2 * BM : BM) + rank * BM + quad * 32 + lane;
+                const int nb = (tq % p.num_n_tiles) * BN + half * (BN / 2);
+                const int ncol = min(BN / 2, p.N - nb);  // N % 8 == 0: a multiple of 16 bytes either way
+                if (row < p.M && ncol > 0) {
+                    const uint8_t* a = reinterpret_cast<const uint8_t*>(p.aux) +
+                                       (static_cast<int64_t>(row) * p.ldaux + nb) * kAuxElem;
+#pragma unroll
+                    for (int l = 0; l < (BN / 2) * kAuxElem / 128; ++l)
+                        if (l * 128 < ncol * kAuxElem) prefetch_l2_line(a + l * 128);
+                }
+            }
+        }
+    };
+    prefetch_aux(w0);
     for (int w = w0; w < num_work; w += wstep) {
+        prefetch_aux(w + wstep);
         const int tile = w / p.split_k;
         const int m_base = (tile / p.num_n_tiles) * (PAIR ? 2 * BM : BM) + rank * BM + quad * 32;
         const int n_base = (tile % p.num_n_tiles) * BN + half * (BN / 2);
