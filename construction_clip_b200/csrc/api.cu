@@ -1,5 +1,6 @@
 // Context, error reporting and tensor-map construction for libb200clip.
 #include <atomic>
+#include <cstdlib>
 #include <cstring>
 
 #include "internal.h"
@@ -10,6 +11,14 @@ static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
 
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("B200CLIP_PDL");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
+}
 
 void set_error(const char* fmt, ...) {
     va_list ap;

@@ -125,6 +125,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
         tma_load_2d(sK, &tm_qkv, &bar_load, d + h * 64, b * S);
         tma_load_2d(sV, &tm_qkv, &bar_load, 2 * d + h * 64, b * S);
     };
+    griddep_launch_dependents();
+    griddep_wait();  // the prologue above overlapped the previous kernel's tail; global memory from here on
     if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < num_work) issue_loads(blockIdx.x);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
@@ -456,6 +458,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         tma_load_2d(sV, &tm_qkv, &bar_load, 2 * d + h * 64, b * S);
         tma_load_2d(sdO, &tm_do, &bar_load, h * 64, b * S);
     };
+    griddep_launch_dependents();
+    griddep_wait();  // the prologue above overlapped the previous kernel's tail; global memory from here on
     if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < num_work) issue_loads(blockIdx.x);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
@@ -957,9 +961,9 @@ extern "C" int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, 
     const int grid = static_cast<int>(work < ctx->num_sms * per_sm ? work : ctx->num_sms * per_sm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (big)
-        attn_fwd_kernel<true><<<grid, kAttnThreads, smem, st>>>(tm, p);
+        B200_CHECK_CUDA(launch_pdl(attn_fwd_kernel<true>, dim3(grid), dim3(kAttnThreads), smem, st, tm, p));
     else
-        attn_fwd_kernel<false><<<grid, kAttnThreads, smem, st>>>(tm, p);
+        B200_CHECK_CUDA(launch_pdl(attn_fwd_kernel<false>, dim3(grid), dim3(kAttnThreads), smem, st, tm, p));
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -1022,9 +1026,9 @@ extern "C" int b200clip_attn_bwd(b200clip_ctx* ctx, const void* qkv, const void*
     const int grid = static_cast<int>(work < ctx->num_sms * per_sm ? work : ctx->num_sms * per_sm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (big)
-        attn_bwd_kernel<true><<<grid, kAttnBwdThreads, smem, st>>>(tm, tmdo, p);
+        B200_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, dim3(grid), dim3(kAttnBwdThreads), smem, st, tm, tmdo, p));
     else
-        attn_bwd_kernel<false><<<grid, kAttnBwdThreads, smem, st>>>(tm, tmdo, p);
+        B200_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, dim3(grid), dim3(kAttnBwdThreads), smem, st, tm, tmdo, p));
     B200_LAUNCH_CHECK();
     return 0;
 }

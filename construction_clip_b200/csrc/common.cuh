@@ -78,6 +78,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #endif
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with the programmatic-stream-serialization attribute (internal.h: launch_pdl) may
+// start while its predecessor in the stream is still draining: its CTAs take over SMs as the
+// predecessor's CTAs retire and run their prologue (barrier init, TMEM allocation, smem zeroing).
+// griddep_wait() blocks until the predecessor grid has completed and its memory is visible -- NO
+// global memory may be touched before it.  griddep_launch_dependents() lets the successor be
+// scheduled as soon as every CTA of this grid has started.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

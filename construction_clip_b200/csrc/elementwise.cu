@@ -182,6 +182,8 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, float* __restric
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    griddep_launch_dependents();
+    griddep_wait();
     if (col < N) {
         for (int r = r0 + warp; r < r1; r += 8) {
             const uint4 u = *reinterpret_cast<const uint4*>(x + static_cast<int64_t>(r) * ldx + col);
@@ -430,8 +432,9 @@ extern "C" int b200clip_colsum(b200clip_ctx* ctx, const void* x, int64_t ldx, fl
     if (gy < 1) gy = 1;
     const int rows_per_block = static_cast<int>(ceil_div(M, gy));
     gy = static_cast<int>(ceil_div(M, rows_per_block));
-    colsum_kernel<<<dim3(gx, gy), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __nv_bfloat16*>(x), ldx, out, static_cast<int>(M), static_cast<int>(N), rows_per_block);
+    B200_CHECK_CUDA(launch_pdl(colsum_kernel, dim3(gx, gy), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                               static_cast<const __nv_bfloat16*>(x), ldx, out, static_cast<int>(M), static_cast<int>(N),
+                               rows_per_block));
     B200_LAUNCH_CHECK();
     return 0;
 }

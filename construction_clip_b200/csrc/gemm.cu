@@ -54,8 +54,8 @@ template <int BN>
 struct GemmCfg {
     static constexpr int kStageBytesB = BN * BK * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
-    static constexpr int kTmemCols = 2 * BN;  // two accumulator stages
+    static constexpr int kStages = (BN >= 192) ? 4 : 6;
+    static constexpr int kTmemCols = (BN > 128) ? 512 : 256;  // two accumulator stages (power of two)
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024;  // + align slack
 };
 
@@ -488,6 +488,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    griddep_launch_dependents();
+    griddep_wait();  // everything above overlapped the previous kernel's tail; global memory from here on
 
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int num_work = num_tiles * p.split_k;
@@ -653,6 +655,8 @@ gemm_pair_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
+    griddep_launch_dependents();
+    griddep_wait();  // everything above overlapped the previous kernel's tail; global memory from here on
 
     const int num_work = p.num_m_tiles * p.num_n_tiles * p.split_k;  // num_m_tiles counts 256-row tiles
     const int w0 = static_cast<int>(blockIdx.x >> 1), wstep = static_cast<int>(gridDim.x >> 1);
@@ -800,7 +804,8 @@ static int launch_pair(b200clip_ctx* ctx, const void* A, int64_t lda, const void
     p.num_n_tiles = static_cast<int>(ceil_div(p.N, 256));
     const int64_t work = static_cast<int64_t>(p.num_m_tiles) * p.num_n_tiles * p.split_k;
     const int clusters = static_cast<int>(work < ctx->num_sms / 2 ? work : ctx->num_sms / 2);
-    gemm_pair_bf16_kernel<A_MN, B_MN><<<2 * clusters, kGemmThreads, kSmemBytesPair, stream>>>(tmA, tmB, p);
+    B200_CHECK_CUDA(launch_pdl(gemm_pair_bf16_kernel<A_MN, B_MN>, dim3(2 * clusters), dim3(kGemmThreads),
+                               kSmemBytesPair, stream, tmA, tmB, p));
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -822,6 +827,9 @@ int init_gemm(b200clip_ctx*) {
     if ((rc = set_attr<256, false, false>())) return rc;
     if ((rc = set_attr<256, false, true>())) return rc;
     if ((rc = set_attr<256, true, true>())) return rc;
+    if ((rc = set_attr<192, false, false>())) return rc;
+    if ((rc = set_attr<192, false, true>())) return rc;
+    if ((rc = set_attr<192, true, true>())) return rc;
     if ((rc = set_attr<128, false, false>())) return rc;
     if ((rc = set_attr<128, false, true>())) return rc;
     if ((rc = set_attr<128, true, true>())) return rc;
@@ -850,7 +858,8 @@ static int launch(b200clip_ctx* ctx, const void* A, int64_t lda, const void* B, 
     p.num_n_tiles = static_cast<int>(ceil_div(p.N, BN));
     const int64_t work = static_cast<int64_t>(p.num_m_tiles) * p.num_n_tiles * p.split_k;
     const int grid = static_cast<int>(work < ctx->num_sms ? work : ctx->num_sms);
-    gemm_bf16_kernel<BN, A_MN, B_MN><<<grid, kGemmThreads, GemmCfg<BN>::kSmemBytes, stream>>>(tmA, tmB, p);
+    B200_CHECK_CUDA(launch_pdl(gemm_bf16_kernel<BN, A_MN, B_MN>, dim3(grid), dim3(kGemmThreads),
+                               GemmCfg<BN>::kSmemBytes, stream, tmA, tmB, p));
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -939,15 +948,37 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
     }();
     const int clusters = ctx->num_sms / 2;
     const int64_t tiles_pair = ceil_div(M, 2 * BM) * ceil_div(N, 256);
-    const bool use_pair = pair_enabled && N >= 256 && M >= 2 * BM && (tiles_pair >= clusters || (out_f32 && epilogue == B200CLIP_EPI_NONE));
+    bool use_pair = pair_enabled && N >= 256 && M >= 2 * BM && (tiles_pair >= clusters || (out_f32 && epilogue == B200CLIP_EPI_NONE));
     // tile width: 256 when that still fills the machine, else 128 for more CTAs
     const int64_t tiles256 = ceil_div(M, BM) * ceil_div(N, 256);
     bool use256 = (N >= 256) && (tiles256 >= ctx->num_sms || (out_f32 && epilogue == B200CLIP_EPI_NONE));
-    if (const char* f = getenv("B200CLIP_FORCE_BN")) {  // tuning / experiments only
-        if (atoi(f) == 128) use256 = false;
-        if (atoi(f) == 256 && N >= 256) use256 = true;
+    bool use192 = false;
+    const char* force_bn = getenv("B200CLIP_FORCE_BN");  // tuning / experiments only
+    if (force_bn) {
+        if (atoi(force_bn) == 128) use256 = false;
+        if (atoi(force_bn) == 256 && N >= 256) use256 = true;
+        if (atoi(force_bn) == 192 && N >= 192) use192 = true, use256 = false;
+    } else if (!(out_f32 && (split_k != 1 || accumulate))) {
+        // One work item per tile (no split-K): pick the tile shape with the smallest makespan
+        // waves x tile-time.  Small per-GPU batches (strong scaling) leave the 256 x 256 pair tiles
+        // with a nearly empty last wave (75 tiles on 74 clusters = 2 waves); 128 x 192 tiles then win.
+        // Tile times relative to a 128 x 256 tile on one SM, measured on the ViT-B/32 layer shapes.
+        const int sms = ctx->num_sms;
+        const double c_pair = (pair_enabled && N >= 256 && M >= 2 * BM)
+                                  ? 0.95 * static_cast<double>(ceil_div(tiles_pair, clusters)) : 1e30;
+        const double c_256 = N >= 256 ? 1.00 * static_cast<double>(ceil_div(tiles256, sms)) : 1e30;
+        const double c_192 = N >= 192 ? 0.80 * static_cast<double>(ceil_div(ceil_div(M, BM) * ceil_div(N, 192), sms)) : 1e30;
+        const double c_128 = 0.62 * static_cast<double>(ceil_div(ceil_div(M, BM) * ceil_div(N, 128), sms));
+        double best = c_pair;
+        use_pair = c_pair < 1e29;
+        use256 = use192 = false;
+        if (c_256 < best - 1e-9) best = c_256, use_pair = false, use256 = true, use192 = false;
+        if (c_192 < best - 1e-9) best = c_192, use_pair = false, use256 = false, use192 = true;
+        if (c_128 < best - 1e-9) best = c_128, use_pair = false, use256 = false, use192 = false;
     }
-    const int64_t tiles = use_pair ? tiles_pair : (use256 ? tiles256 : ceil_div(M, BM) * ceil_div(N, 128));
+    const int64_t tiles = use_pair ? tiles_pair
+                          : use192 ? ceil_div(M, BM) * ceil_div(N, 192)
+                                   : (use256 ? tiles256 : ceil_div(M, BM) * ceil_div(N, 128));
     if (split_k <= 0) split_k = out_f32 ? choose_split_k(tiles, p.kb_total, use_pair ? clusters : ctx->num_sms) : 1;
     if (split_k > p.kb_total) split_k = p.kb_total;
     p.kb_per_split = static_cast<int>(ceil_div(p.kb_total, split_k));
@@ -961,6 +992,11 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
         if (!amn && !bmn) return launch_pair<false, false>(ctx, A, lda, B, ldb, p, st);
         if (!amn && bmn) return launch_pair<false, true>(ctx, A, lda, B, ldb, p, st);
         return launch_pair<true, true>(ctx, A, lda, B, ldb, p, st);
+    }
+    if (use192) {
+        if (!amn && !bmn) return launch<192, false, false>(ctx, A, lda, B, ldb, p, st);
+        if (!amn && bmn) return launch<192, false, true>(ctx, A, lda, B, ldb, p, st);
+        return launch<192, true, true>(ctx, A, lda, B, ldb, p, st);
     }
     if (use256) {
         if (!amn && !bmn) return launch<256, false, false>(ctx, A, lda, B, ldb, p, st);

@@ -1,5 +1,6 @@
 // Host-side internals shared by the translation units of libb200clip.
 #pragma once
+#include <utility>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -59,6 +60,26 @@ void set_error(const char* fmt, ...);
         b200::count_launch();                \
         B200_CHECK_CUDA(cudaGetLastError()); \
     } while (0)
+
+// Kernel launch with programmatic dependent launch enabled (see common.cuh: the kernel must call
+// griddep_wait() before its first global-memory access).  B200CLIP_PDL=0 falls back to plain
+// stream-ordered launches.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // 2-D bf16 tensor map, 128-byte swizzle.  dim0 = innermost extent (elements), dim1 = rows,
 // pitch in elements; box = (box0 <= 64, box1 <= 256).

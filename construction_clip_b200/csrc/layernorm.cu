@@ -52,6 +52,8 @@ layernorm_fwd_kernel(const TX* __restrict__ x, int64_t ldx, const int32_t* __res
     const int lane = threadIdx.x & 31;
     const int warps_per_block = kLnThreads / 32;
     const int nvec = d >> 3;
+    griddep_launch_dependents();
+    griddep_wait();
     for (int r = blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < rows; r += gridDim.x * warps_per_block) {
         const int64_t src = row_index ? row_index[r] : r;
         float v[NV][8];
@@ -169,6 +171,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const T
     __nv_bfloat16* s_gamma = reinterpret_cast<__nv_bfloat16*>(s_ln + static_cast<size_t>(3) * d * sizeof(float));
     uint8_t* wbase = s_ln + static_cast<size_t>(3) * d * sizeof(float) + yb + static_cast<size_t>(warp) * 2u * stage_bytes;
     for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) s_acc[i] = 0.f;
+    griddep_launch_dependents();
+    griddep_wait();  // global memory from here on
     for (int i = threadIdx.x; i < d; i += blockDim.x) s_gamma[i] = gamma[i];
     if (lane == 0) {
         mbar_init(&s_bar[warp][0], 1);
@@ -310,10 +314,8 @@ static cudaError_t launch_ln_bwd(int grid, int threads, size_t smem, cudaStream_
         if (e != cudaSuccess) return e;
         configured = smem;
     }
-    layernorm_bwd_kernel<NU, TX, COLSUM><<<grid, threads, smem, st>>>(dy, lddy, x, ldx, row_index, gamma, mean, rstd,
-                                                                       dres, lddres, dx, lddx, dgamma, dbeta, dx_colsum,
-                                                                       rows, d);
-    return cudaSuccess;
+    return launch_pdl(layernorm_bwd_kernel<NU, TX, COLSUM>, dim3(grid), dim3(threads), smem, st, dy, lddy, x, ldx,
+                      row_index, gamma, mean, rstd, dres, lddres, dx, lddx, dgamma, dbeta, dx_colsum, rows, d);
 }
 
 }  // namespace b200
@@ -345,10 +347,11 @@ extern "C" int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t 
     const int64_t want = ceil_div(rows, wpb);
     const int grid = static_cast<int>(want < ctx->num_sms * 8 ? want : ctx->num_sms * 8);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t le = cudaSuccess;
     B200_CHECK_ARG((x_dtype == B200CLIP_DT_BF16 || x_dtype == B200CLIP_DT_F32) &&
                        (y_dtype == B200CLIP_DT_BF16 || y_dtype == B200CLIP_DT_F32), "layernorm_fwd: bad dtype");
 #define CALL_T(NV, TX, TY)                                                                                         \
-    layernorm_fwd_kernel<NV, TX, TY><<<grid, kLnThreads, 0, st>>>(                                                 \
+    le = launch_pdl(layernorm_fwd_kernel<NV, TX, TY>, dim3(grid), dim3(kLnThreads), 0, st,                         \
         static_cast<const TX*>(x), ldx, row_index, static_cast<const __nv_bfloat16*>(neg_row),                     \
         static_cast<const __nv_bfloat16*>(add), static_cast<int>(add ? add_period : 1),                            \
         static_cast<const __nv_bfloat16*>(gamma), static_cast<const __nv_bfloat16*>(beta), static_cast<TY*>(y),    \
@@ -368,6 +371,7 @@ extern "C" int b200clip_layernorm_fwd(b200clip_ctx* ctx, const void* x, int64_t 
     LN_DISPATCH(d, CALL);
 #undef CALL
 #undef CALL_T
+    B200_CHECK_CUDA(le);
     B200_LAUNCH_CHECK();
     return 0;
 }
