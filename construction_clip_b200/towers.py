@@ -83,7 +83,7 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None):
     return x
 
 
-def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved):
+def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved, on_layer_done=None):
     """Bias gradients are column sums of the gradient stream; they are produced by the kernel that
     WRITES each tensor (GEMM epilogue ``colsum`` / LayerNorm-backward ``dx_colsum``) instead of by
     separate reduction passes -- only dqkv (written by the attention backward) and the incoming dy
@@ -112,6 +112,8 @@ def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved):
         dy = O.layernorm_bwd(dh1, s.x, W[p + "ln_1.weight"], s.mean1, s.rstd1, G[p + "ln_1.weight"],
                              G[p + "ln_1.bias"], dres=dx2, dx_colsum=prev_bias)
         saved.blocks[i] = None  # release this layer's activations
+        if on_layer_done is not None:  # every parameter gradient of layers >= i is final now
+            on_layer_done(i)
     return dy
 
 
@@ -170,14 +172,14 @@ def vision_fwd(W, cfg, image, save: bool):
     return feat, saved
 
 
-def vision_bwd(W, G, cfg, saved: TowerSaved, dfeat):
+def vision_bwd(W, G, cfg, saved: TowerSaved, dfeat, on_layer_done=None):
     e = saved.extra
     B, n, d = e["B"], cfg.vision_tokens, cfg.vision_width
     H = d // 64
     pooled, mean, rstd = e["head"]
     dx = _pool_project_bwd(W, G, dfeat, e["x_last"], e["cls_rows"], "ln_post.weight", "ln_post.bias", "proj", pooled,
                            mean, rstd)
-    dx = blocks_bwd(W, G, "transformer.", cfg.vision_layers, dx, B, n, H, False, saved)
+    dx = blocks_bwd(W, G, "transformer.", cfg.vision_layers, dx, B, n, H, False, saved, on_layer_done)
     dpre = O.layernorm_bwd(dx, e["pre"], W["ln_pre.weight"], e["mean0"], e["rstd0"], G["ln_pre.weight"],
                            G["ln_pre.bias"])
     dpatch = O.vision_assemble_bwd(dpre, B, n, G["positional_embedding"], G["class_embedding"])
@@ -200,14 +202,14 @@ def text_fwd(W, cfg, text, save: bool):
     return feat, saved
 
 
-def text_bwd(W, G, cfg, saved: TowerSaved, dfeat):
+def text_bwd(W, G, cfg, saved: TowerSaved, dfeat, on_layer_done=None):
     e = saved.extra
     B, S = e["B"], e["S"]
     H = cfg.transformer_heads
     pooled, mean, rstd = e["head"]
     dx = _pool_project_bwd(W, G, dfeat, e["x_last"], e["eot"], "ln_final.weight", "ln_final.bias", "text_projection",
                            pooled, mean, rstd)
-    dx = blocks_bwd(W, G, "transformer.", cfg.transformer_layers, dx, B, S, H, True, saved)
+    dx = blocks_bwd(W, G, "transformer.", cfg.transformer_layers, dx, B, S, H, True, saved, on_layer_done)
     O.embed_tokens_bwd(e["ids"], dx, G["token_embedding.weight"], G["positional_embedding"])
 
 

@@ -113,6 +113,55 @@ def clip_contrastive_loss(model, image, text, group=None, return_correct=False):
 
 
 # ------------------------------------------------------------------------------------------------
+def _plan_chunks(store, world, min_elems=1 << 20):
+    """Cuts a tower's flat parameter range into contiguous chunks (a, b, ready_layer).  ``ready_layer``
+    = L >= 0: every gradient inside is final once the backward of transformer block L is done;
+    -1: only at the end of the tower's backward (embeddings, conv1, ln_pre and the first blocks).
+    Head parameters (ln_post / proj / ln_final / text_projection) are final before the first block;
+    tiny runs are merged into a neighbour that becomes final no earlier.  Every chunk length divides
+    by ``world`` (reduce-scatter / all-gather in equal shards), else the plan is one chunk."""
+    layers = 1 + max((int(n.split("resblocks.")[1].split(".")[0]) for n, *_ in store.entries if "resblocks." in n),
+                     default=-1)
+    bounds = sorted({layers // 6, layers // 3 + layers // 12, 2 * layers // 3}) if layers >= 6 else []
+    bounds = [L for L in bounds if L > 0]
+    head = ("ln_post.", "proj", "ln_final.", "text_projection")
+
+    def group(name):  # 0 = final at the end, g >= 1 = final after block bounds[g-1]
+        if "resblocks." in name:
+            i = int(name.split("resblocks.")[1].split(".")[0])
+            return sum(i >= L for L in bounds)
+        return len(bounds) if name.startswith(head) else 0
+
+    runs = []  # [start, end, group]
+    ends = [o for _, _, o, _ in store.entries][1:] + [store.total]
+    for (name, _, o, _), e in zip(store.entries, ends):
+        g = group(name)
+        if runs and runs[-1][2] == g:
+            runs[-1][1] = e
+        else:
+            runs.append([o, e, g])
+    merged = True
+    while merged and len(runs) > 1:  # fold small runs into a neighbour (the union is final at the later of the two)
+        merged = False
+        for i, (a, b, g) in enumerate(runs):
+            if b - a < min_elems:
+                j = i - 1 if i > 0 and (i == len(runs) - 1 or runs[i - 1][2] <= runs[i + 1][2]) else i + 1
+                lo, hi = min(i, j), max(i, j)
+                runs[lo:hi + 1] = [[runs[lo][0], runs[hi][1], min(runs[lo][2], runs[hi][2])]]
+                merged = True
+                break
+    out = []
+    for a, b, g in runs:
+        tag = bounds[g - 1] if g > 0 else -1
+        if out and out[-1][2] == tag:
+            out[-1] = (out[-1][0], b, tag)
+        else:
+            out.append((a, b, tag))
+    if any((b - a) % world for a, b, _ in out):
+        return [(0, store.total, -1)]
+    return out
+
+
 class ClipTrainer:
     """Owns flat fp32 gradients / master weights / Adam moments for both towers and runs the
     whole training step with library kernels.  Hyper-parameters default to the reference's
@@ -134,17 +183,36 @@ class ClipTrainer:
         # the sum of its 1/N slice), AdamW runs on that slice only (fp32 master / moments are 1/N the
         # size) and the updated bf16 weights are all-gathered in place -- less NVLink traffic than an
         # all-reduce (fp32 down, bf16 back) and 1/N of the optimiser's HBM traffic.
+        # The flat buffers are cut into a few contiguous CHUNKS whose gradients become final at different
+        # points of the backward pass (layers finish last-to-first); a chunk's collectives + update run
+        # on a side stream as soon as it is final, under the rest of the backward (see _plan_chunks).
         self.sharded = bool(shard_optimizer) and self.world > 1
-        self.grads, self.master, self.m, self.v, self.shard = {}, {}, {}, {}, {}
+        self.grads, self.master, self.m, self.v, self.chunks, self.chunk_ready = {}, {}, {}, {}, {}, {}
+        self._comm_streams = {}
+        # the two towers' collectives are issued from two streams; a second communicator keeps the text
+        # tower's early chunks from queueing behind the vision tower's last one (one FIFO per communicator)
+        self._tower_group = {"visual": group, "text": group}
+        if self.sharded:
+            ranks = dist.get_process_group_ranks(group) if group is not None else list(range(self.world))
+            self._tower_group["text"] = dist.new_group(ranks=ranks)
         for k, st in self.stores.items():
             st.sync()
             self.grads[k] = torch.zeros(st.total, device=self.device, dtype=f32)
-            n = st.total // self.world if self.sharded else st.total
-            lo = self.rank * n if self.sharded else 0
-            self.shard[k] = (lo, n)
-            self.master[k] = st.w[lo:lo + n].float()
-            self.m[k] = torch.zeros(n, device=self.device, dtype=f32)
-            self.v[k] = torch.zeros(n, device=self.device, dtype=f32)
+            ranges = _plan_chunks(st, self.world) if self.sharded else [(0, st.total, -1)]
+            chunks, moff = [], 0
+            for a, b, ready in ranges:
+                n = (b - a) // self.world if self.sharded else b - a
+                chunks.append((a, b, moff, n, ready))  # flat range, offset / length of this rank's slice in master/m/v
+                moff += n
+            self.chunks[k] = chunks
+            self.chunk_ready[k] = {}
+            for j, c in enumerate(chunks):
+                if c[4] >= 0:
+                    self.chunk_ready[k].setdefault(c[4], []).append(j)
+            self.master[k] = torch.cat([st.w[a + self.rank * n * int(self.sharded):][:n].float()
+                                        for a, b, _, n, _ in chunks])
+            self.m[k] = torch.zeros(moff, device=self.device, dtype=f32)
+            self.v[k] = torch.zeros(moff, device=self.device, dtype=f32)
         self.G = {k: self.stores[k].grad_views(self.grads[k]) for k in self.stores}
         self.ls_master = model.logit_scale.detach().to(f32).reshape(1).clone()
         self.ls_m = torch.zeros(1, device=self.device, dtype=f32)
@@ -221,20 +289,18 @@ class ClipTrainer:
             d_txt.record_stream(stt)
         work = []
         hyper = self._hyper if self._hyper_live else None
-        with torch.cuda.stream(sv):
-            T.vision_bwd(Wv, self.G["visual"], cfg, saved_i, d_img)
-            if self.world > 1:
-                if fused_update and self.sharded:
-                    self._sharded_update("visual", hyper)
-                else:
-                    work.append(dist.all_reduce(self.grads["visual"], group=self.group, async_op=True))
-        with torch.cuda.stream(stt):
-            T.text_bwd(Wt, self.G["text"], cfg, saved_t, d_txt)
-            if self.world > 1:
-                if fused_update and self.sharded:
-                    self._sharded_update("text", hyper)
-                else:
-                    work.append(dist.all_reduce(self.grads["text"], group=self.group, async_op=True))
+        fused = fused_update and self.sharded
+        for k, s_tower, bwd, W_, saved_, dfeat in (("visual", sv, T.vision_bwd, Wv, saved_i, d_img),
+                                                   ("text", stt, T.text_bwd, Wt, saved_t, d_txt)):
+            with torch.cuda.stream(s_tower):
+                bwd(W_, self.G[k], cfg, saved_, dfeat, self._chunk_callback(k, s_tower, hyper) if fused else None)
+                if self.world > 1:
+                    if fused:
+                        self._sharded_update(k, hyper, ready=-1)  # what only becomes final at the end
+                        if k in self._comm_streams:
+                            s_tower.wait_stream(self._comm_streams[k])
+                    else:
+                        work.append(dist.all_reduce(self.grads[k], group=self.group, async_op=True))
         if two:
             main.wait_stream(sv)
             main.wait_stream(stt)
@@ -251,14 +317,39 @@ class ClipTrainer:
         return dict(lr=self.current_lr() if hyper is None else 0.0, beta1=b1, beta2=b2, eps=self.eps,
                     weight_decay=self.wd, grad_scale=1.0, step=self.step_count if hyper is None else 0, hyper=hyper)
 
-    def _sharded_update(self, k, hyper):
-        """reduce-scatter(grad) -> AdamW on the local shard -> all-gather(bf16 weights), on the current stream."""
+    def _sharded_update(self, k, hyper, ready=None, only=None):
+        """reduce-scatter(grad) -> AdamW on the local shard -> all-gather(bf16 weights) on the current
+        stream, for the chunks of tower ``k`` selected by ``only`` (indices) / ``ready`` (their
+        ready-layer tag) -- all of them by default."""
         st = self.stores[k]
-        lo, n = self.shard[k]
-        gshard = self.grads[k][lo:lo + n]
-        dist.reduce_scatter_tensor(gshard, self.grads[k], group=self.group)
-        O.adamw(self.master[k], st.w[lo:lo + n], gshard, self.m[k], self.v[k], **self._adam_args(hyper))
-        dist.all_gather_into_tensor(st.w, st.w[lo:lo + n], group=self.group)
+        g = self.grads[k]
+        for j, (a, b, moff, n, tag) in enumerate(self.chunks[k]):
+            if (only is not None and j not in only) or (ready is not None and tag != ready):
+                continue
+            lo = a + self.rank * n
+            grp = self._tower_group[k]
+            dist.reduce_scatter_tensor(g[lo:lo + n], g[a:b], group=grp)
+            O.adamw(self.master[k][moff:moff + n], st.w[lo:lo + n], g[lo:lo + n], self.m[k][moff:moff + n],
+                    self.v[k][moff:moff + n], **self._adam_args(hyper))
+            dist.all_gather_into_tensor(st.w[a:b], st.w[lo:lo + n], group=grp)
+
+    def _chunk_callback(self, k, tower_stream, hyper):
+        """Called by the tower's backward after each transformer block: chunks that just became final
+        are reduced / updated / re-gathered on a side stream while the backward goes on."""
+        table = self.chunk_ready[k]
+        if not table:
+            return None
+        if k not in self._comm_streams:
+            self._comm_streams[k] = torch.cuda.Stream(device=self.device)
+        side = self._comm_streams[k]
+
+        def done(layer):
+            idx = table.get(layer)
+            if idx:
+                side.wait_stream(tower_stream)
+                with torch.cuda.stream(side):
+                    self._sharded_update(k, hyper, only=idx)
+        return done
 
     def optimizer_step(self, hyper=None, towers=True, _count=True):
         """AdamW on both flat buffers + logit_scale.  ``hyper`` (device float[3]) carries lr and the
@@ -355,7 +446,8 @@ class ClipTrainer:
                 full = self.master[k]
                 if self.sharded:
                     full = torch.empty(st.total, device=self.device, dtype=f32)
-                    dist.all_gather_into_tensor(full, self.master[k], group=self.group)
+                    for a, b, moff, n, _ in self.chunks[k]:
+                        dist.all_gather_into_tensor(full[a:b], self.master[k][moff:moff + n], group=self.group)
                 for name, p, o, s in st.entries:
                     if p.data_ptr() != st.W[name].data_ptr():
                         n = math.prod(s)
