@@ -28,7 +28,18 @@ for _ in range(3):
     tr.step(img, tok)
 e1.record()
 torch.cuda.synchronize()
-print(f"wall per step (no profiler): {e0.elapsed_time(e1) / 3:.2f} ms")
+print(f"wall per step (eager, no profiler): {e0.elapsed_time(e1) / 3:.2f} ms")
+tr.enable_cuda_graph(True)
+for _ in range(3):
+    tr.step(img, tok)
+torch.cuda.synchronize()
+e0.record()
+for _ in range(10):
+    tr.step(img, tok)
+e1.record()
+torch.cuda.synchronize()
+print(f"wall per step (CUDA graph replay): {e0.elapsed_time(e1) / 10:.2f} ms")
+tr.enable_cuda_graph(False)
 from torch.profiler import ProfilerActivity, profile
 with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof:
     tr.step(img, tok)
