@@ -485,8 +485,11 @@ class ClipTrainer:
         cur.wait_event(ev)
         img_d.record_stream(cur)
         txt_d.record_stream(cur)
-        self._staged = stage(*next_batch) if next_batch is not None else None
+        # enqueue this step's GPU work FIRST: cudaMemcpyAsync of a large pinned batch can hold the host
+        # thread for about the DMA time (measured 1.9 ms for 77 MB, more when copies queue up), and that
+        # must not delay the launch of the step the GPU is waiting for
         loss = self.step(img_d, txt_d)
+        self._staged = stage(*next_batch) if next_batch is not None else None
         slot = self._loss_host[self._loss_slot:self._loss_slot + 1]
         self._loss_slot = (self._loss_slot + 1) % 64
         slot.copy_(loss.reshape(1), non_blocking=True)
