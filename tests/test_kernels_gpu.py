@@ -35,6 +35,7 @@ GEMM_SHAPES = [
     (128, 128, 64), (128, 256, 64), (128, 128, 256), (256, 512, 192), (1600, 2304, 768), (1232, 512, 2048),
     (77, 136, 72), (3000, 768, 3072), (32, 512, 768), (6400, 3072, 768),
     (20000, 768, 512), (19999, 520, 200),   # CTA-pair (cta_group::2) kernel: >= 74 tiles of 256 x 256, ragged edges
+    (6400, 768, 768), (9856, 512, 1536), (6390, 776, 520),   # 128 x 192 tiles (75-78 pair tiles = 2 waves otherwise)
 ]
 
 
@@ -69,7 +70,7 @@ def test_gemm_tn_wgrad(ops, M, N, K):
     _close(out, 2 * ref, 2e-3 * math.sqrt(K), 1e-3, f"gemm TN accumulate {M}x{N}x{K}")
 
 
-@pytest.mark.parametrize("M", [1000, 20000])   # 20000 rows -> CTA-pair kernel
+@pytest.mark.parametrize("M", [1000, 6400, 20000])   # 6400 rows -> 128 x 192 tiles, 20000 rows -> CTA-pair kernel
 def test_gemm_epilogues(ops, M):
     from construction_clip_b200 import lib as L
     N, K = 768, 512
@@ -98,7 +99,17 @@ def test_gemm_epilogues(ops, M):
     _close(ops.gemm(view, w), view.float() @ w.float().t(), 3e-2, 1e-2, "strided A")
 
 
-@pytest.mark.parametrize("rows,d", [(1600, 768), (1232, 512), (77, 128), (515, 1024)])
+def test_split_f32_to_bf16(ops):
+    """hi + lo carries an fp32 GEMM operand at ~16 mantissa bits (the feature-projection input)."""
+    x = torch.randn(1000, 768, device="cuda") * 3
+    hi, lo = ops.split_f32_to_bf16(x)
+    assert hi.dtype == bf16 and lo.dtype == bf16
+    assert torch.equal(hi, x.to(bf16))
+    rel = ((hi.float() + lo.float() - x).abs() / x.abs().clamp_min(1e-6)).max().item()
+    assert rel < 2.0 ** -15, rel
+
+
+@pytest.mark.parametrize("rows,d", [(1600, 768), (1232, 512), (77, 128), (515, 1024), (20000, 768), (3, 2048)])
 def test_layernorm(ops, rows, d):
     x = _rand((rows, d), 2.0, seed=1)
     g = (1 + 0.1 * torch.randn(d, device="cuda")).to(bf16)
