@@ -184,6 +184,9 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
                                                int lane) {
     using Op = EpiOperands<EPI, OUT_F32>;
     using OutT = typename std::conditional<OUT_F32, float, __nv_bfloat16>::type;
+    // column sums of C ride along in the QuickGELU' epilogue (c_fc bias gradient) and in the plain bf16
+    // one (out_proj dgrad: the V third of in_proj_bias' gradient is the column sum of d(attention out))
+    constexpr bool kColsum = (EPI == B200CLIP_EPI_QUICKGELU_BWD) || (EPI == B200CLIP_EPI_NONE && !OUT_F32);
     const int rrow = lane >> 3, rch = lane & 7;
     const int col = col0 + rch * 4;
     const bool col_ok = FULL ? true : col < p.N;
@@ -265,7 +268,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
             }
         }
         if (ok) {
-            if constexpr (EPI == B200CLIP_EPI_QUICKGELU_BWD) {  // the only flavour that carries a fused column sum
+            if constexpr (kColsum) {  // flavours that can carry a fused column sum (bias gradients)
                 cs0 += x0; cs1 += x1; cs2 += x2; cs3 += x3;
             }
             if constexpr (OUT_F32) {
@@ -280,7 +283,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
         cptr += rstride;
         if constexpr (PRE) pptr += rstride;
     }
-    if constexpr (EPI == B200CLIP_EPI_QUICKGELU_BWD) {
+    if constexpr (kColsum) {
         if (p.colsum != nullptr) {  // warp-uniform
             // lanes l, l^8, l^16, l^24 hold the same 4 columns for different rows
             cs0 += __shfl_xor_sync(0xffffffffu, cs0, 8);  cs1 += __shfl_xor_sync(0xffffffffu, cs1, 8);
@@ -920,9 +923,9 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
     }
     B200_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias not 16B aligned");
     B200_CHECK_ARG(preact == nullptr || (reinterpret_cast<uintptr_t>(preact) & 15) == 0, "gemm: preact misaligned");
-    B200_CHECK_ARG(colsum == nullptr || ((reinterpret_cast<uintptr_t>(colsum) & 15) == 0 &&
-                                         epilogue == B200CLIP_EPI_QUICKGELU_BWD && !out_f32),
-                   "gemm: colsum is fused into the EPI_QUICKGELU_BWD (bf16) epilogue only, 16-byte aligned");
+    B200_CHECK_ARG(colsum == nullptr || ((reinterpret_cast<uintptr_t>(colsum) & 15) == 0 && !out_f32 &&
+                                         (epilogue == B200CLIP_EPI_QUICKGELU_BWD || epilogue == B200CLIP_EPI_NONE)),
+                   "gemm: colsum is fused into the bf16 EPI_NONE / EPI_QUICKGELU_BWD epilogues only, 16-byte aligned");
 
     GemmParams p{};
     p.C = C;

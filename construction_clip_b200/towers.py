@@ -86,8 +86,8 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None):
 def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved, on_layer_done=None):
     """Bias gradients are column sums of the gradient stream; they are produced by the kernel that
     WRITES each tensor (GEMM epilogue ``colsum`` / LayerNorm-backward ``dx_colsum``) instead of by
-    separate reduction passes -- only dqkv (written by the attention backward) and the incoming dy
-    of the last block use the stand-alone colsum kernel."""
+    separate reduction passes -- only the Q third of dqkv (written by the attention backward) and the
+    incoming dy of the last block use the stand-alone colsum kernel."""
     O.colsum(dy, G[_blk(prefix, layers - 1) + "mlp.c_proj.bias"])
     for i in reversed(range(layers)):
         p = _blk(prefix, i)
@@ -102,9 +102,17 @@ def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved, on_
                               G[p + "ln_2.bias"], dres=dy, dx_colsum=G[p + "attn.out_proj.bias"])
         # ---- attention branch: x2 = x + out_proj(attn(in_proj(ln_1(x))))
         O.linear_wgrad(dx2, s.a, G[p + "attn.out_proj.weight"])
-        da = O.linear_dgrad(dx2, W[p + "attn.out_proj.weight"])
+        # in_proj_bias gradient = column sums of dqkv = [dQ | dK | dV] without reading all of dqkv again:
+        #   V third: sum_kv dV = sum_q (P^T dO) = sum_q dO because softmax rows sum to one -> the column
+        #            sums of `da`, produced by this dgrad GEMM's epilogue;
+        #   K third: sum_k dK = sum_q (sum_k dS[q,k]) Q[q] = 0 exactly (rows of dS sum to zero; a key
+        #            bias shifts every score of a row equally) -> stays at the zero of the gradient buffer;
+        #   Q third: a real reduction, the stand-alone colsum over the first d columns of dqkv.
+        gb = G[p + "attn.in_proj_bias"]
+        d_model = gb.numel() // 3
+        da = O.linear_dgrad(dx2, W[p + "attn.out_proj.weight"], colsum=gb[2 * d_model:])
         dqkv = O.attn_bwd(s.qkv, s.a, s.lse, da, B, S, H, causal)
-        O.colsum(dqkv, G[p + "attn.in_proj_bias"])
+        O.colsum(dqkv[:, :d_model], gb[:d_model])
         O.linear_wgrad(dqkv, s.h1, G[p + "attn.in_proj_weight"])
         dh1 = O.linear_dgrad(dqkv, W[p + "attn.in_proj_weight"])
         # dx of this LayerNorm is the dy of block i-1: its column sums are that block's c_proj bias gradient

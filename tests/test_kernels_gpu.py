@@ -78,6 +78,9 @@ def test_gemm_epilogues(ops, M):
     bias, aux = _rand((N,), seed=9), _rand((M, N), seed=10)
     base = a.float() @ w.float().t() + bias.float()
     _close(ops.gemm(a, w, bias=bias), base, 3e-2, 1e-2, "bias")
+    cs0 = torch.zeros(N, device="cuda")
+    _close(ops.gemm(a, w, bias=bias, colsum=cs0), base, 3e-2, 1e-2, "bias + colsum")
+    _close(cs0, base.sum(0), 2e-2 * math.sqrt(M), 1e-2, "fused colsum of C (plain epilogue)")
     pre = torch.empty((M, N), device="cuda", dtype=bf16)
     got = ops.gemm(a, w, bias=bias, epilogue=L.EPI_QUICKGELU, preact=pre)
     _close(pre, base, 3e-2, 1e-2, "preact")
