@@ -243,7 +243,8 @@ __global__ void __launch_bounds__(256)
 loss_bwd_g_kernel(const float* __restrict__ img_all, const float* __restrict__ txt_all,
                   const float* __restrict__ logit_scale, const float* __restrict__ lse_i_all,
                   const float* __restrict__ lse_t_all, const float* __restrict__ grad_out, int row0, int Bl, int Bg,
-                  int E, __nv_bfloat16* __restrict__ G, float* __restrict__ coef_out, float* __restrict__ d_logit_scale) {
+                  int E, __nv_bfloat16* __restrict__ G, int ldg, float* __restrict__ coef_out,
+                  float* __restrict__ d_logit_scale) {
     __shared__ __align__(16) float Xs[TK][TS + 4];
     __shared__ __align__(16) float Ys[TK][TS + 4];
     __shared__ float s_red[8];
@@ -260,7 +261,7 @@ loss_bwd_g_kernel(const float* __restrict__ img_all, const float* __restrict__ t
     const float coef = g * s / (2.0f * Bg);
     if (blockIdx.x == 0 && blockIdx.y == 0 && dir == 0 && threadIdx.x == 0) *coef_out = coef;
     const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
-    __nv_bfloat16* Gd = G + static_cast<int64_t>(dir) * Bl * Bg;
+    __nv_bfloat16* Gd = G + static_cast<int64_t>(dir) * Bl * ldg;  // row pitch ldg = Bg rounded up to 8 (TMA pitch rule)
     float dsum = 0.f;
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
@@ -279,15 +280,11 @@ loss_bwd_g_kernel(const float* __restrict__ img_all, const float* __restrict__ t
             }
         }
         const int j = j0 + tx * 4;
-        if (j + 3 < Bg && (Bg & 3) == 0) {
+        if (j + 3 < ldg) {  // columns Bg .. ldg-1 are written as zeros (gv = 0 there)
             uint2 o;
             o.x = pack_bf16(gv[0], gv[1]);
             o.y = pack_bf16(gv[2], gv[3]);
-            *reinterpret_cast<uint2*>(Gd + static_cast<int64_t>(i) * Bg + j) = o;
-        } else {
-#pragma unroll
-            for (int b = 0; b < 4; ++b)
-                if (j + b < Bg) Gd[static_cast<int64_t>(i) * Bg + j + b] = __float2bfloat16_rn(gv[b]);
+            *reinterpret_cast<uint2*>(Gd + static_cast<int64_t>(i) * ldg + j) = o;
         }
     }
     if (dir == 0 && d_logit_scale != nullptr) {
@@ -322,7 +319,8 @@ extern "C" int64_t b200clip_clip_loss_workspace_bytes(b200clip_ctx* ctx, int64_t
     if (ctx == nullptr || Bl <= 0 || Bg <= 0 || E <= 0) return -1;
     const int ns = loss_nsplit(Bl, Bg, ctx->num_sms);
     const size_t fwd = align256(sizeof(float) * 2 * ns * Bl) * 2 + align256(sizeof(float) * ns * Bl) * 2;
-    const size_t bwd = align256(2ull * Bl * Bg * 2) + 2 * align256(static_cast<size_t>(Bg) * E * 2) + 256;
+    const size_t ldg = static_cast<size_t>((Bg + 7) / 8 * 8);
+    const size_t bwd = align256(2ull * Bl * ldg * 2) + 2 * align256(static_cast<size_t>(Bg) * E * 2) + 256;
     return static_cast<int64_t>(fwd > bwd ? fwd : bwd);
 }
 
@@ -380,21 +378,22 @@ extern "C" int b200clip_clip_loss_bwd(b200clip_ctx* ctx, const float* img_all, c
     B200_CHECK_ARG(img_all && txt_all && logit_scale && lse_i_all && lse_t_all && d_img && d_txt && workspace,
                    "clip_loss_bwd: null pointer");
     B200_CHECK_ARG(Bl > 0 && Bg > 0 && row0 >= 0 && row0 + Bl <= Bg && E > 0 && E % TK == 0, "clip_loss_bwd: bad shape");
-    B200_CHECK_ARG(Bg % 8 == 0 && E % 8 == 0, "clip_loss_bwd: Bg and E must be multiples of 8 (tensor-core GEMM operands)");
+    B200_CHECK_ARG(E % 8 == 0, "clip_loss_bwd: E must be a multiple of 8 (tensor-core GEMM operand)");
+    const int64_t ldg = (Bg + 7) / 8 * 8;  // any global batch (the reference trains with 9): G's pitch is padded
     B200_CHECK_ARG(workspace_bytes >= b200clip_clip_loss_workspace_bytes(ctx, Bl, Bg, E), "clip_loss_bwd: workspace too small");
     uint8_t* w = static_cast<uint8_t*>(workspace);
     __nv_bfloat16* G = reinterpret_cast<__nv_bfloat16*>(w);
-    w += align256(2ull * Bl * Bg * 2);
+    w += align256(2ull * Bl * ldg * 2);
     __nv_bfloat16* img_bf = reinterpret_cast<__nv_bfloat16*>(w);
     w += align256(static_cast<size_t>(Bg) * E * 2);
     __nv_bfloat16* txt_bf = reinterpret_cast<__nv_bfloat16*>(w);
     w += align256(static_cast<size_t>(Bg) * E * 2);
     float* coef = reinterpret_cast<float*>(w);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    dim3 grid(static_cast<unsigned>(ceil_div(Bg, TS)), static_cast<unsigned>(ceil_div(Bl, TS)), 2);
+    dim3 grid(static_cast<unsigned>(ceil_div(ldg, TS)), static_cast<unsigned>(ceil_div(Bl, TS)), 2);
     loss_bwd_g_kernel<<<grid, 256, 0, st>>>(img_all, txt_all, logit_scale, lse_i_all, lse_t_all, grad_out,
                                             static_cast<int>(row0), static_cast<int>(Bl), static_cast<int>(Bg),
-                                            static_cast<int>(E), G, coef, d_logit_scale);
+                                            static_cast<int>(E), G, static_cast<int>(ldg), coef, d_logit_scale);
     B200_LAUNCH_CHECK();
     int rc;
     if ((rc = b200clip_cast_f32_to_bf16(ctx, img_all, img_bf, Bg * E, stream))) return rc;
@@ -402,10 +401,10 @@ extern "C" int b200clip_clip_loss_bwd(b200clip_ctx* ctx, const float* img_all, c
     // d_img[Bl,E] = coef * G0[Bl,Bg] @ txt_all[Bg,E] ; d_txt = coef * G1 @ img_all   (B operand MN-major)
     B200_CHECK_CUDA(cudaMemsetAsync(d_img, 0, sizeof(float) * Bl * E, st));
     B200_CHECK_CUDA(cudaMemsetAsync(d_txt, 0, sizeof(float) * Bl * E, st));
-    if ((rc = b200clip_gemm_bf16(ctx, G, Bg, B200CLIP_MAJOR_K, txt_bf, E, B200CLIP_MAJOR_MN, d_img, E, B200CLIP_DT_F32,
+    if ((rc = b200clip_gemm_bf16(ctx, G, ldg, B200CLIP_MAJOR_K, txt_bf, E, B200CLIP_MAJOR_MN, d_img, E, B200CLIP_DT_F32,
                                  nullptr, nullptr, 0, nullptr, coef, nullptr, Bl, E, Bg, B200CLIP_EPI_NONE, 0, 1, stream)))
         return rc;
-    if ((rc = b200clip_gemm_bf16(ctx, G + Bl * Bg, Bg, B200CLIP_MAJOR_K, img_bf, E, B200CLIP_MAJOR_MN, d_txt, E,
+    if ((rc = b200clip_gemm_bf16(ctx, G + Bl * ldg, ldg, B200CLIP_MAJOR_K, img_bf, E, B200CLIP_MAJOR_MN, d_txt, E,
                                  B200CLIP_DT_F32, nullptr, nullptr, 0, nullptr, coef, nullptr, Bl, E, Bg, B200CLIP_EPI_NONE, 0,
                                  1, stream)))
         return rc;

@@ -278,7 +278,8 @@ def test_colsum_l2norm_cast_assemble_bwd(ops):
     _close(dcls, v[:, 0].sum(0), 1e-3, 1e-3, "assemble dcls")
 
 
-@pytest.mark.parametrize("Bg,E,row0,Bl", [(64, 512, 0, 64), (200, 512, 0, 200), (1024, 512, 256, 128), (96, 768, 32, 64)])
+@pytest.mark.parametrize("Bg,E,row0,Bl", [(64, 512, 0, 64), (200, 512, 0, 200), (1024, 512, 256, 128), (96, 768, 32, 64),
+                                          (9, 512, 0, 9), (27, 512, 9, 9)])   # the reference trains with batch 9
 def test_clip_loss(ops, Bg, E, row0, Bl):
     torch.manual_seed(Bg)
     img = torch.nn.functional.normalize(torch.randn(Bg, E, device="cuda"), dim=1)

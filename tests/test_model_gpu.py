@@ -182,6 +182,35 @@ def test_fused_loss_and_trainer_match_autograd():
     assert losses[-1] < loss2.item()
 
 
+def test_pooled_last_block_is_exact():
+    """Running the last block's out_proj / ln_2 / MLP on the pooled (CLS / EOT) tokens only must give
+    the same features and the same gradients as running them on every token and discarding the rest."""
+    from construction_clip_b200 import towers
+    from construction_clip_b200.train import ClipTrainer
+    name, B = "ViT-B/32", 9
+    orc = oracle_model(name)
+    img, tok = _inputs(name, B, B, 30)
+    out = {}
+    for flag in (True, False):
+        towers.POOL_LAST_BLOCK = flag
+        try:
+            m = device_model(name, orc).train()
+            with torch.no_grad():
+                fi, ft = m.encode_image(img.cuda()), m.encode_text(tok.cuda())
+            tr = ClipTrainer(m)
+            loss = tr.forward_backward(img.cuda(), tok.cuda())
+            out[flag] = (fi.float(), ft.float(), loss.item(), {k: g.clone() for k, g in tr.grads.items()})
+        finally:
+            towers.POOL_LAST_BLOCK = True
+    fi1, ft1, l1, g1 = out[True]
+    fi0, ft0, l0, g0 = out[False]
+    assert cosine_rows(fi1.cpu(), fi0.cpu()).min() > 0.99999 and cosine_rows(ft1.cpu(), ft0.cpu()).min() > 0.99999
+    assert abs(l1 - l0) <= 1e-4 * abs(l0)
+    for k in g1:
+        assert cosine(g1[k].cpu(), g0[k].cpu()) > 0.9999, k
+        assert abs(g1[k].norm().item() / g0[k].norm().item() - 1) < 1e-2, k
+
+
 def test_fp32_parameters_and_state_dict_roundtrip():
     """model.float() (what upstream's clip.load does on CPU) keeps working: the kernels read a
     bf16 shadow refreshed from the fp32 parameters; gradients come back in fp32."""
