@@ -284,6 +284,41 @@ def test_bench_reference_arm_runs_on_cpu():
                         "--warmup", "1", "--model", "tiny"], capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert r.returncode == 0, r.stderr[-2000:]
     import json
-    line = json.loads(r.stdout.strip().splitlines()[-1])
+    out_lines = r.stdout.strip().splitlines()
+    assert len(out_lines) == 1, f"bench.py must print exactly one stdout line, got {len(out_lines)}"
+    line = json.loads(out_lines[0])
     assert line["impl"] == "reference" and line["value"] > 0 and line["cpu_baseline"]["kind"] == "port"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["unit"] == "pairs/s"
+
+
+@pytest.mark.parametrize("name", ["ViT-B/32", "ViT-L/14", "tiny"])
+def test_optimizer_chunk_plan(name):
+    """The trainer's chunked reduce-scatter plan: contiguous cover of the flat buffer, every chunk
+    divisible by the world size, and no parameter lands in a chunk that is reduced before the
+    parameter's gradient is final (blocks finish last-to-first; embeddings / conv1 / ln_pre at the end)."""
+    import types
+    from construction_clip_b200.model import CLIP, CONFIGS
+    from construction_clip_b200.train import _plan_chunks
+    m = CLIP(CONFIGS[name])
+    for which in ("visual", "text"):
+        entries, off = [], 0
+        for n, p in m._tower_named_params(which):
+            entries.append((n, p, off, tuple(p.shape)))
+            off += (p.numel() + 63) // 64 * 64
+        unit = 64 * 840
+        store = types.SimpleNamespace(entries=entries, total=(off + unit - 1) // unit * unit)
+        for world in (2, 3, 4, 8):
+            plan = _plan_chunks(store, world)
+            assert plan[0][0] == 0 and plan[-1][1] == store.total
+            for (a, b, tag), nxt in zip(plan, plan[1:] + [None]):
+                assert b > a and (b - a) % world == 0
+                if nxt is not None:
+                    assert nxt[0] == b
+            head = ("ln_post.", "proj", "ln_final.", "text_projection")
+            for n, _, o, _ in entries:
+                tag = next(t for a, b, t in plan if a <= o < b)
+                if "resblocks." in n:
+                    layer = int(n.split("resblocks.")[1].split(".")[0])
+                    assert tag <= layer, (n, tag)      # reduced only after block `tag` <= this block is done
+                elif not n.startswith(head):
+                    assert tag == -1, (n, tag)         # embeddings, conv1, ln_pre: final at the very end
