@@ -30,7 +30,27 @@ struct AttnParams {
     __nv_bfloat16* out;      // fwd: [B*S, H*64] ; bwd: dqkv [B*S, 3*H*64]
     int B, S, H, causal;
     int npad;  // S rounded up to a multiple of 16
+    // packed ("varlen") rows: sample b owns rows cu[b] .. cu[b+1]-1 (at most S of them) of qkv / out /
+    // dqkv, and lse is indexed [row * H + h].  nullptr: every sample owns S rows, lse [(b*H + h)*S + r].
+    const int32_t* cu;
 };
+
+// rows and length of work item b
+template <bool VARLEN>
+__device__ __forceinline__ void item_rows(const AttnParams& p, int b, int& row0, int& len) {
+    if constexpr (VARLEN) {
+        row0 = __ldg(p.cu + b);
+        len = __ldg(p.cu + b + 1) - row0;
+        len = len < 0 ? 0 : (len > p.S ? p.S : len);
+    } else {
+        row0 = b * p.S;
+        len = p.S;
+    }
+}
+template <bool VARLEN>
+__device__ __forceinline__ int64_t lse_index(const AttnParams& p, int b, int h, int row0, int r) {
+    return VARLEN ? static_cast<int64_t>(row0 + r) * p.H + h : (static_cast<int64_t>(b) * p.H + h) * p.S + r;
+}
 
 // Shared-memory tiles are COMPACT: npad rows x 128 B (one row per token, 128-byte swizzled).  The
 // tensor core reads 128 rows for an M=128 A operand, i.e. past the tile into whatever follows;
@@ -73,7 +93,7 @@ __device__ __forceinline__ int warp_limit(int row0, int S, int causal) {
 }
 
 // ------------------------------------------------------------------------------------------------
-template <bool BIG>  // BIG: S > 64 (P needs two 64-column tiles)
+template <bool BIG, bool VARLEN = false>  // BIG: S > 64 (P needs two 64-column tiles); VARLEN: packed rows (p.cu)
 __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
@@ -116,14 +136,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
     const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
     const float sc = 0.125f * kLog2e;
     const int num_work = p.B * H;
-    const int lim = row_limit(r, S, p.causal);                        // attended columns of this row
-    const int wchunks = (warp_limit(warp * 32, S, p.causal) + 15) >> 4;  // 16-column chunks this warp visits
+    constexpr bool varlen = VARLEN;
+    int hw = 0;  // varlen: chunks of this warp's P rows that may still hold a previous item's values
     auto issue_loads = [&](int w) {
         const int b = w / H, h = w - b * H;
+        int row0, len;
+        item_rows<VARLEN>(p, b, row0, len);
         mbar_arrive_expect_tx(&bar_load, load_bytes);
-        tma_load_2d(sQ, &tm_qkv, &bar_load, h * 64, b * S);
-        tma_load_2d(sK, &tm_qkv, &bar_load, d + h * 64, b * S);
-        tma_load_2d(sV, &tm_qkv, &bar_load, 2 * d + h * 64, b * S);
+        tma_load_2d(sQ, &tm_qkv, &bar_load, h * 64, row0);
+        tma_load_2d(sK, &tm_qkv, &bar_load, d + h * 64, row0);
+        tma_load_2d(sV, &tm_qkv, &bar_load, 2 * d + h * 64, row0);
     };
     griddep_launch_dependents();
     griddep_wait();  // the prologue above overlapped the previous kernel's tail; global memory from here on
@@ -131,6 +153,10 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
         const int b = w / H, h = w - b * H;
+        int row0, Si;
+        item_rows<VARLEN>(p, b, row0, Si);
+        const int lim = row_limit(r, Si, p.causal);                            // attended columns of this row
+        const int wchunks = (warp_limit(warp * 32, Si, p.causal) + 15) >> 4;   // 16-column chunks this warp visits
         if (threadIdx.x == 0) {
             mbar_wait(&bar_load, it & 1u);
             tc_fence_after();
@@ -165,13 +191,23 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
             }
             const float msc = mx * sc;
             sum = 0.f;
-            for (int ci = 0; ci < wchunks; ++ci) {
+            // packed rows: the mask differs between work items, so positions a previous (longer) item
+            // wrote and this one masks are cleared explicitly, up to the warp's high-water mark
+            const int nproc = (varlen && hw > wchunks) ? hw : wchunks;
+            for (int ci = 0; ci < nproc; ++ci) {
                 const int c0 = ci << 4;
                 uint32_t v[16];
                 __syncwarp();
-                tmem_ld_32x16(trow + c0, v);
-                tmem_ld_wait();
-                if (c0 < lim) {  // else: masked in every work item, the tile position stays zero
+                if (ci < wchunks) {  // warp-uniform
+                    tmem_ld_32x16(trow + c0, v);
+                    tmem_ld_wait();
+                }
+                if (varlen && (ci >= wchunks || c0 >= lim)) {
+                    if (r < npad) {
+                        *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, c0 >> 3)) = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, (c0 >> 3) + 1)) = make_uint4(0u, 0u, 0u, 0u);
+                    }
+                } else if (c0 < lim) {  // else (fixed length): masked in every work item, the position stays zero
                     float e[16];
                     if (c0 + 16 <= lim) {
 #pragma unroll
@@ -189,8 +225,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
                         pack_bf16(e[8], e[9]), pack_bf16(e[10], e[11]), pack_bf16(e[12], e[13]), pack_bf16(e[14], e[15]));
                 }
             }
-            if (p.lse != nullptr && r < S)  // log2-domain: p = exp2(s * sc - lse)
-                p.lse[(static_cast<int64_t>(b) * H + h) * S + r] = msc + log2f(sum);
+            hw = wchunks;
+            if (p.lse != nullptr && r < Si)  // log2-domain: p = exp2(s * sc - lse)
+                p.lse[lse_index<VARLEN>(p, b, h, row0, r)] = msc + log2f(sum);
         }  // warp_live
         fence_proxy_async_smem();
         tc_fence_before();
@@ -210,13 +247,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
             __syncwarp();
             tc_fence_after();
             const float inv = 1.0f / sum;
-            __nv_bfloat16* dst = p.out + (static_cast<int64_t>(b) * S + r) * d + h * 64;
+            __nv_bfloat16* dst = p.out + static_cast<int64_t>(row0 + r) * d + h * 64;
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld_32x32(trow + c0, v);
                 tmem_ld_wait();
-                if (r < S) {
+                if (r < Si) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         uint4 o;
@@ -397,7 +434,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParam
 // Backward.  With the forward's row log-sum-exp and D = rowsum(dO o O) known up front there is no
 // row reduction left: ONE pass over (S, dP) produces P and dS.  Two threads share a row (they take
 // different 16-column chunks), 8 warps per CTA, 2 CTAs per SM.
-template <bool BIG>
+template <bool BIG, bool VARLEN = false>
 __global__ void __launch_bounds__(kAttnBwdThreads)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                 const AttnParams p) {
@@ -447,16 +484,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const uint32_t idesc_nn = make_idesc_bf16(128, 64, 0, 1);     // dQ = dS K
     const float sc = 0.125f * kLog2e;
     const int num_work = p.B * H;
-    const bool live = r < S;
-    const int lim = row_limit(r, S, p.causal);                               // attended columns of this row
-    const int wchunks = (warp_limit((warp & 3) * 32, S, p.causal) + 15) >> 4;  // 16-column chunks this warp pair visits
+    constexpr bool varlen = VARLEN;
+    int hw = 0;  // varlen: chunks of this warp pair's P / dS rows that may still hold a previous item's values
     auto issue_loads = [&](int w) {
         const int b = w / H, h = w - b * H;
+        int row0, len;
+        item_rows<VARLEN>(p, b, row0, len);
         mbar_arrive_expect_tx(&bar_load, load_bytes);
-        tma_load_2d(sQ, &tm_qkv, &bar_load, h * 64, b * S);
-        tma_load_2d(sK, &tm_qkv, &bar_load, d + h * 64, b * S);
-        tma_load_2d(sV, &tm_qkv, &bar_load, 2 * d + h * 64, b * S);
-        tma_load_2d(sdO, &tm_do, &bar_load, h * 64, b * S);
+        tma_load_2d(sQ, &tm_qkv, &bar_load, h * 64, row0);
+        tma_load_2d(sK, &tm_qkv, &bar_load, d + h * 64, row0);
+        tma_load_2d(sV, &tm_qkv, &bar_load, 2 * d + h * 64, row0);
+        tma_load_2d(sdO, &tm_do, &bar_load, h * 64, row0);
     };
     griddep_launch_dependents();
     griddep_wait();  // the prologue above overlapped the previous kernel's tail; global memory from here on
@@ -464,14 +502,19 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
         const int b = w / H, h = w - b * H;
+        int row0, Si;
+        item_rows<VARLEN>(p, b, row0, Si);
+        const bool live = r < Si;
+        const int lim = row_limit(r, Si, p.causal);                                // attended columns of this row
+        const int wchunks = (warp_limit((warp & 3) * 32, Si, p.causal) + 15) >> 4;  // 16-column chunks this warp pair visits
         // row statistics from the forward, fetched while the tiles are in flight; the two threads of a
         // row each take half of the 64 columns of D = rowsum(dO o O)
         float m2 = 0.f;
         uint4 ov[4];
         if (live) {
-            m2 = p.lse[(static_cast<int64_t>(b) * H + h) * S + r];
+            m2 = p.lse[lse_index<VARLEN>(p, b, h, row0, r)];
             const uint4* op =
-                reinterpret_cast<const uint4*>(p.o + (static_cast<int64_t>(b) * S + r) * d + h * 64) + half * 4;
+                reinterpret_cast<const uint4*>(p.o + static_cast<int64_t>(row0 + r) * d + h * 64) + half * 4;
 #pragma unroll
             for (int c = 0; c < 4; ++c) ov[c] = __ldg(op + c);
         }
@@ -515,14 +558,27 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
             // single pass: P = exp2(S*sc - lse), dS = P o (dP - D) / 8 -> swizzled smem (bf16); the two
             // warps of a row group take alternate 16-column chunks
-            for (int ci = half; ci < wchunks; ci += 2) {
+            // packed rows: the mask differs between work items, so positions a previous (longer) item
+            // wrote and this one masks are cleared explicitly, up to the warp pair's high-water mark
+            const int nproc = (varlen && hw > wchunks) ? hw : wchunks;
+            for (int ci = half; ci < nproc; ci += 2) {
                 const int c0 = ci << 4;
                 uint32_t v[16], g[16];
                 __syncwarp();  // tcgen05.ld is warp-collective: reconverge after the per-row branches
-                tmem_ld_32x16(trow + c0, v);
-                tmem_ld_32x16(trow + 128 + c0, g);
-                tmem_ld_wait();
-                if (c0 < lim) {  // else: masked in every work item, the tile positions stay zero
+                if (ci < wchunks) {  // warp-uniform
+                    tmem_ld_32x16(trow + c0, v);
+                    tmem_ld_32x16(trow + 128 + c0, g);
+                    tmem_ld_wait();
+                }
+                if (varlen && (ci >= wchunks || c0 >= lim)) {
+                    if (r < npad) {
+                        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+                        *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, c0 >> 3)) = z;
+                        *reinterpret_cast<uint4*>(p_chunk(sP, TB, r, (c0 >> 3) + 1)) = z;
+                        *reinterpret_cast<uint4*>(p_chunk(sdS, TB, r, c0 >> 3)) = z;
+                        *reinterpret_cast<uint4*>(p_chunk(sdS, TB, r, (c0 >> 3) + 1)) = z;
+                    }
+                } else if (c0 < lim) {  // else (fixed length): masked in every work item, the positions stay zero
                     float pe[16], ds[16];
                     if (c0 + 16 <= lim) {
 #pragma unroll
@@ -548,6 +604,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                         pack_bf16(ds[8], ds[9]), pack_bf16(ds[10], ds[11]), pack_bf16(ds[12], ds[13]), pack_bf16(ds[14], ds[15]));
                 }
             }
+            hw = wchunks;
         }
         fence_proxy_async_smem();
         tc_fence_before();
@@ -580,7 +637,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             tc_fence_after();
             // six 32-column output chunks per row: dQ (TMEM 128..191), dK (64..127), dV (0..63);
             // the two threads of a row take three each
-            __nv_bfloat16* dst = p.out + (static_cast<int64_t>(b) * S + r) * (3 * d) + h * 64;
+            __nv_bfloat16* dst = p.out + static_cast<int64_t>(row0 + r) * (3 * d) + h * 64;
 #pragma unroll
             for (int q = 0; q < 3; ++q) {
                 const int oc = half * 3 + q;         // 0..5
@@ -888,6 +945,14 @@ int init_attention(b200clip_ctx*) {
         e = cudaFuncSetAttribute(attn_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem(false, 64));
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(attn_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem(true, 128));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(false, 64));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(true, 128));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_bwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem(false, 64));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attn_bwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bwd_smem(true, 128));
     if (e != cudaSuccess) {
         set_error("cudaFuncSetAttribute(attention): %s", cudaGetErrorString(e));
         return B200CLIP_ERR_CUDA;
@@ -964,6 +1029,79 @@ extern "C" int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, 
         B200_CHECK_CUDA(launch_pdl(attn_fwd_kernel<true>, dim3(grid), dim3(kAttnThreads), smem, st, tm, p));
     else
         B200_CHECK_CUDA(launch_pdl(attn_fwd_kernel<false>, dim3(grid), dim3(kAttnThreads), smem, st, tm, p));
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+// Packed rows: sample b owns rows cu[b] .. cu[b+1]-1 (1 .. S_max <= 128 of them) of qkv [total_rows, 3*H*64].
+extern "C" int b200clip_attn_fwd_varlen(b200clip_ctx* ctx, const void* qkv, void* out, float* lse, const int32_t* cu,
+                                        int64_t B, int64_t S_max, int64_t H, int64_t total_rows, int causal,
+                                        void* stream) {
+    int rc = check_attn_args(ctx, qkv, out, B, S_max, H, false);
+    if (rc) return rc;
+    B200_CHECK_ARG(cu != nullptr && total_rows > 0 && total_rows < (1ll << 31) && S_max <= 128,
+                   "attn_fwd_varlen: needs cu, total_rows and S_max <= 128");
+    B200_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "attention: out not 16-byte aligned");
+    CUtensorMap tm;
+    if ((rc = make_tmap_bf16_2d(ctx, &tm, qkv, 3 * H * 64, total_rows, 3 * H * 64, 64, static_cast<uint32_t>(S_max))))
+        return rc;
+    AttnParams p{};
+    p.out = static_cast<__nv_bfloat16*>(out);
+    p.lse = lse;
+    p.B = static_cast<int>(B);
+    p.S = static_cast<int>(S_max);
+    p.H = static_cast<int>(H);
+    p.causal = causal ? 1 : 0;
+    p.npad = static_cast<int>((S_max + 15) / 16 * 16);
+    p.cu = cu;
+    const bool big = S_max > 64;
+    const int smem = fwd_smem(big, p.npad);
+    const int per_sm = ctas_per_sm(smem, big ? 128 : 64, 8);
+    const int64_t work = B * H;
+    const int grid = static_cast<int>(work < ctx->num_sms * per_sm ? work : ctx->num_sms * per_sm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (big)
+        B200_CHECK_CUDA(launch_pdl(attn_fwd_kernel<true, true>, dim3(grid), dim3(kAttnThreads), smem, st, tm, p));
+    else
+        B200_CHECK_CUDA(launch_pdl(attn_fwd_kernel<false, true>, dim3(grid), dim3(kAttnThreads), smem, st, tm, p));
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200clip_attn_bwd_varlen(b200clip_ctx* ctx, const void* qkv, const void* out, const float* lse,
+                                        const void* dout, void* dqkv, const int32_t* cu, int64_t B, int64_t S_max,
+                                        int64_t H, int64_t total_rows, int causal, void* stream) {
+    int rc = check_attn_args(ctx, qkv, dout, B, S_max, H, false);
+    if (rc) return rc;
+    B200_CHECK_ARG(out && lse && cu && total_rows > 0 && total_rows < (1ll << 31) && S_max <= 128,
+                   "attn_bwd_varlen: needs out, lse, cu, total_rows and S_max <= 128");
+    B200_CHECK_ARG(dqkv && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                   "attention: dqkv / out null or misaligned");
+    CUtensorMap tm, tmdo;
+    if ((rc = make_tmap_bf16_2d(ctx, &tm, qkv, 3 * H * 64, total_rows, 3 * H * 64, 64, static_cast<uint32_t>(S_max))))
+        return rc;
+    if ((rc = make_tmap_bf16_2d(ctx, &tmdo, dout, H * 64, total_rows, H * 64, 64, static_cast<uint32_t>(S_max))))
+        return rc;
+    AttnParams p{};
+    p.o = static_cast<const __nv_bfloat16*>(out);
+    p.lse = const_cast<float*>(lse);
+    p.out = static_cast<__nv_bfloat16*>(dqkv);
+    p.B = static_cast<int>(B);
+    p.S = static_cast<int>(S_max);
+    p.H = static_cast<int>(H);
+    p.causal = causal ? 1 : 0;
+    p.npad = static_cast<int>((S_max + 15) / 16 * 16);
+    p.cu = cu;
+    const bool big = S_max > 64;
+    const int smem = bwd_smem(big, p.npad);
+    const int per_sm = ctas_per_sm(smem, 256, 2);
+    const int64_t work = B * H;
+    const int grid = static_cast<int>(work < ctx->num_sms * per_sm ? work : ctx->num_sms * per_sm);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (big)
+        B200_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true, true>, dim3(grid), dim3(kAttnBwdThreads), smem, st, tm, tmdo, p));
+    else
+        B200_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false, true>, dim3(grid), dim3(kAttnBwdThreads), smem, st, tm, tmdo, p));
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -34,6 +34,8 @@ SIGNATURES = {
     "b200clip_layernorm_bwd": [_p, _p, _l, _p, _l, _p, _p, _p, _p, _p, _l, _p, _l, _p, _p, _p, _l, _l, _i, _p],
     "b200clip_attn_fwd": [_p, _p, _p, _p, _l, _l, _l, _i, _p],
     "b200clip_attn_bwd": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _i, _p],
+    "b200clip_attn_fwd_varlen": [_p, _p, _p, _p, _p, _l, _l, _l, _l, _i, _p],
+    "b200clip_attn_bwd_varlen": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _i, _p],
     "b200clip_embed_tokens_fwd": [_p, _p, _p, _p, _p, _i, _p, _l, _l, _l, _l, _p],
     "b200clip_embed_tokens_bwd": [_p, _p, _p, _p, _p, _l, _l, _l, _l, _p],
     "b200clip_im2col_patch": [_p, _p, _i, _p, _l, _l, _l, _l, _p],

@@ -28,6 +28,13 @@ bf16, f32, i32 = torch.bfloat16, torch.float32, torch.int32
 # exists for A/B timing and for the test that proves both settings give the same features and gradients.
 POOL_LAST_BLOCK = os.environ.get("B200CLIP_POOL_LAST_BLOCK", "1") != "0"
 
+# EXPERIMENTAL, off by default (not yet validated on hardware): pack every caption to its EOT + 1 tokens.
+# Under upstream's causal mask nothing after the EOT token can reach the pooled feature and those
+# positions receive exactly-zero gradients, so the text tower can run on sum(lengths) rows instead of
+# B x 77 (the same dead-code argument as POOL_LAST_BLOCK, applied to every block).  Needs a host sync
+# per call (dynamic row count), so the step is not captured into a CUDA graph in this mode.
+PACK_TEXT = os.environ.get("B200CLIP_PACK_TEXT", "0") == "1"
+
 
 @dataclass
 class BlockSaved:
@@ -60,7 +67,7 @@ def _blk(prefix: str, i: int) -> str:
 
 # ------------------------------------------------------------------------------------------------
 # clip.model.ResidualAttentionBlock:  x = x + attn(ln_1(x)) ; x = x + c_proj(QuickGELU(c_fc(ln_2(x))))
-def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None, pool_rows=None):
+def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None, pool_rows=None, cu=None):
     """``pool_rows`` (int32 [B], rows of ``x``): the only tokens of the LAST block's output that the
     tower uses (CLS rows for ``visual``: ``x[:, 0, :]``; EOT rows for text: ``x[arange, argmax]``).
     Every token of the last block still feeds attention through K and V, but its out_proj, ln_2 and
@@ -72,16 +79,16 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None, 
         p = _blk(prefix, i)
         save = saved is not None
         if pool_rows is not None and i == layers - 1:
-            return _last_block_fwd(W, p, x, B, S, H, causal, saved, pool_rows)
+            return _last_block_fwd(W, p, x, B, S, H, causal, saved, pool_rows, cu)
         if save:
             h1, mean1, rstd1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"], want_stats=True)
         else:
             h1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"])
         qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
         if save:
-            a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True)
+            a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True, cu=cu)
         else:
-            a, lse = O.attn_fwd(qkv, B, S, H, causal), None
+            a, lse = O.attn_fwd(qkv, B, S, H, causal, cu=cu), None
         x2 = O.linear_fwd(a, W[p + "attn.out_proj.weight"], W[p + "attn.out_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x,
                           out_dtype=f32)
         if save:
@@ -99,16 +106,16 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None, 
     return x
 
 
-def _last_block_fwd(W, p, x, B, S, H, causal, saved, pool_rows):
+def _last_block_fwd(W, p, x, B, S, H, causal, saved, pool_rows, cu=None):
     save = saved is not None
     if save:
         h1, mean1, rstd1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"], want_stats=True)
         qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
-        a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True)
+        a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True, cu=cu)
     else:
         h1, mean1, rstd1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"]), None, None
         qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
-        a, lse = O.attn_fwd(qkv, B, S, H, causal), None
+        a, lse = O.attn_fwd(qkv, B, S, H, causal, cu=cu), None
     rows = pool_rows.long()
     a_p = a.index_select(0, rows)   # [B, d] bf16
     x_p = x.index_select(0, rows)   # [B, d] fp32 residual stream at the pooled tokens
@@ -128,7 +135,7 @@ def _last_block_fwd(W, p, x, B, S, H, causal, saved, pool_rows):
     return y
 
 
-def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved, on_layer_done=None):
+def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved, on_layer_done=None, cu=None):
     """Bias gradients are column sums of the gradient stream; they are produced by the kernel that
     WRITES each tensor (GEMM epilogue ``colsum`` / LayerNorm-backward ``dx_colsum``) instead of by
     separate reduction passes -- only the Q third of dqkv (written by the attention backward) and the
@@ -159,7 +166,7 @@ def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved, on_
         if s.pool is not None:  # pooled last block: the gradients of every other token are exactly zero
             da = torch.zeros((s.a.shape[0], d_model), device=da.device, dtype=bf16).index_copy_(0, s.pool, da)
             dx2 = torch.zeros((s.a.shape[0], d_model), device=da.device, dtype=bf16).index_copy_(0, s.pool, dx2)
-        dqkv = O.attn_bwd(s.qkv, s.a, s.lse, da, B, S, H, causal)
+        dqkv = O.attn_bwd(s.qkv, s.a, s.lse, da, B, S, H, causal, cu=cu)
         O.colsum(dqkv[:, :d_model], gb[:d_model])
         O.linear_wgrad(dqkv, s.h1, G[p + "attn.in_proj_weight"])
         dh1 = O.linear_dgrad(dqkv, W[p + "attn.in_proj_weight"])
@@ -254,12 +261,22 @@ def text_fwd(W, cfg, text, save: bool):
     ids = text.to(i32).contiguous()
     x, eot = O.embed_tokens_fwd(ids, W["token_embedding.weight"], W["positional_embedding"], out_dtype=f32)
     saved = TowerSaved() if save else None
-    x = blocks_fwd(W, "transformer.", cfg.transformer_layers, x, B, S, H, True, saved, eot if POOL_LAST_BLOCK else None)
+    cu = rows_src = None
+    if PACK_TEXT:  # keep positions 0 .. EOT of every caption only (see PACK_TEXT above)
+        pos_eot = eot - torch.arange(B, device=ids.device, dtype=i32) * S
+        cu = torch.zeros(B + 1, device=ids.device, dtype=i32)
+        cu[1:] = torch.cumsum(pos_eot + 1, 0)
+        keep = torch.arange(S, device=ids.device, dtype=i32)[None, :] <= pos_eot[:, None]
+        rows_src = keep.reshape(-1).nonzero().squeeze(1)     # int64 [sum(lengths)], host sync (dynamic shape)
+        x = x.index_select(0, rows_src)
+        eot = (cu[1:] - 1).contiguous()                       # the EOT rows of the packed layout
+    x = blocks_fwd(W, "transformer.", cfg.transformer_layers, x, B, S, H, True, saved,
+                   eot if POOL_LAST_BLOCK else None, cu)
     if POOL_LAST_BLOCK:
         eot = None  # x is already [B, d]: the EOT tokens
     feat, head = _pool_project_fwd(W, x, eot, "ln_final.weight", "ln_final.bias", "text_projection", save)
     if save:
-        saved.extra = dict(B=B, S=S, ids=ids, eot=eot, x_last=x, head=head)
+        saved.extra = dict(B=B, S=S, ids=ids, eot=eot, x_last=x, head=head, cu=cu, rows_src=rows_src)
     return feat, saved
 
 
@@ -270,7 +287,9 @@ def text_bwd(W, G, cfg, saved: TowerSaved, dfeat, on_layer_done=None):
     pooled, mean, rstd = e["head"]
     dx = _pool_project_bwd(W, G, dfeat, e["x_last"], e["eot"], "ln_final.weight", "ln_final.bias", "text_projection",
                            pooled, mean, rstd)
-    dx = blocks_bwd(W, G, "transformer.", cfg.transformer_layers, dx, B, S, H, True, saved, on_layer_done)
+    dx = blocks_bwd(W, G, "transformer.", cfg.transformer_layers, dx, B, S, H, True, saved, on_layer_done, e.get("cu"))
+    if e.get("rows_src") is not None:  # packed rows -> [B*S, d]; the dropped positions have zero gradient
+        dx = torch.zeros((B * S, dx.shape[1]), device=dx.device, dtype=bf16).index_copy_(0, e["rows_src"], dx)
     O.embed_tokens_bwd(e["ids"], dx, G["token_embedding.weight"], G["positional_embedding"])
 
 

@@ -498,7 +498,7 @@ class ClipTrainer:
     def step(self, image, text):
         """One optimisation step on this rank's slice (image [Bl,3,R,R], text [Bl,77]) of the
         global batch; returns the global mean loss as a device tensor (no host sync)."""
-        if self._use_graph:
+        if self._use_graph and not T.PACK_TEXT:  # packed text has a data-dependent row count: eager launches
             return self._graph_step(image, text)
         self.step_count += 1
         loss = self.forward_backward(image, text, fused_update=True)

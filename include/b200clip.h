@@ -133,6 +133,16 @@ int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, float* lse,
 int b200clip_attn_bwd(b200clip_ctx* ctx, const void* qkv, const void* out, const float* lse, const void* dout,
                       void* dqkv, void* workspace, int64_t workspace_bytes, int64_t B, int64_t S, int64_t H, int causal,
                       void* stream);
+/* Packed ("varlen") form for the text tower: sample b owns rows cu[b] .. cu[b+1]-1 (int32 [B+1], at most
+ * S_max <= 128 rows each) of qkv / out / dout / dqkv [total_rows, ...]; lse is fp32 [total_rows * H],
+ * indexed [row * H + head].  With upstream's causal mask nothing after a caption's EOT token can reach
+ * its pooled feature (clip/model.py: build_attention_mask + x[arange, text.argmax(-1)]), so those
+ * positions need not exist at all: pack each caption to EOT + 1 tokens. */
+int b200clip_attn_fwd_varlen(b200clip_ctx* ctx, const void* qkv, void* out, float* lse, const int32_t* cu, int64_t B,
+                             int64_t S_max, int64_t H, int64_t total_rows, int causal, void* stream);
+int b200clip_attn_bwd_varlen(b200clip_ctx* ctx, const void* qkv, const void* out, const float* lse, const void* dout,
+                             void* dqkv, const int32_t* cu, int64_t B, int64_t S_max, int64_t H, int64_t total_rows,
+                             int causal, void* stream);
 
 /* ---- token_embedding(text) + positional_embedding  (clip.model.CLIP.encode_text) ---------------
  * ids int32 [B,S]; table bf16 [V,d]; pos bf16 [S,d]; out bf16 or f32 (out_dtype) [B*S,d]; eot_row int32 [B] receives

@@ -3,6 +3,9 @@ statement of the same operator on the same seeded inputs.  Tolerances are bf16-l
 inputs are bf16-exact, accumulation is fp32, outputs are rounded to bf16 once."""
 import math
 
+import numpy as np
+import os
+
 import pytest
 import torch
 
@@ -192,6 +195,30 @@ def test_attention_fwd_bwd(ops, B, S, H, causal):
     ref.backward(dout.float())
     dqkv = ops.attn_bwd(qkv, out, lse, dout, B, S, H, causal)
     _close(dqkv, qr.grad, 4e-2, 4e-2, "attn bwd")
+
+
+EXPERIMENTAL = os.environ.get("B200CLIP_TEST_EXPERIMENTAL", "0") == "1"
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="packed-text attention is experimental (set B200CLIP_TEST_EXPERIMENTAL=1)")
+@pytest.mark.parametrize("lens,S,H,causal", [([77, 5, 33, 64, 1, 76, 17], 77, 8, True), ([50, 3, 20], 50, 2, False),
+                                             ([9] * 40 + [70, 2, 31], 77, 8, True)])
+def test_attention_varlen(ops, lens, S, H, causal):
+    """Packed rows: every sample attends inside its own cu[b] .. cu[b+1]-1 rows only."""
+    B, d = len(lens), H * 64
+    cu = torch.tensor([0] + list(np.cumsum(lens)), device="cuda", dtype=torch.int32)
+    M = int(cu[-1])
+    qkv = _rand((M, 3 * d), 1.5, seed=M)
+    dout = _rand((M, d), seed=M + 1)
+    out, lse = ops.attn_fwd(qkv, B, S, H, causal, want_lse=True, cu=cu)
+    dqkv = ops.attn_bwd(qkv, out, lse, dout, B, S, H, causal, cu=cu)
+    for b, n in enumerate(lens):
+        a = int(cu[b])
+        qr = qkv[a:a + n].float().requires_grad_(True)
+        ref = _attn_ref(qr, 1, n, H, causal)
+        _close(out[a:a + n], ref, 2e-2, 2e-2, f"varlen attn fwd sample {b} (len {n})")
+        ref.backward(dout[a:a + n].float())
+        _close(dqkv[a:a + n], qr.grad, 4e-2, 4e-2, f"varlen attn bwd sample {b} (len {n})")
 
 
 @pytest.mark.parametrize("B,S,H,causal", [(2, 197, 12, False), (1, 257, 16, False), (1, 577, 4, False), (2, 200, 2, True),

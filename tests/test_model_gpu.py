@@ -5,6 +5,7 @@ identical zero-shot arg-max (asserted on rows whose oracle top-2 margin exceeds 
 tolerance), loss within 1e-3 relative.  Gradients: cosine >= 0.99 per parameter tensor against
 oracle autograd, norms within 5 %."""
 import math
+import os
 
 import numpy as np
 import pytest
@@ -205,6 +206,37 @@ def test_pooled_last_block_is_exact():
     fi1, ft1, l1, g1 = out[True]
     fi0, ft0, l0, g0 = out[False]
     assert cosine_rows(fi1.cpu(), fi0.cpu()).min() > 0.99999 and cosine_rows(ft1.cpu(), ft0.cpu()).min() > 0.99999
+    assert abs(l1 - l0) <= 1e-4 * abs(l0)
+    for k in g1:
+        assert cosine(g1[k].cpu(), g0[k].cpu()) > 0.9999, k
+        assert abs(g1[k].norm().item() / g0[k].norm().item() - 1) < 1e-2, k
+
+
+@pytest.mark.skipif(os.environ.get("B200CLIP_TEST_EXPERIMENTAL", "0") != "1",
+                    reason="packed text tower is experimental (set B200CLIP_TEST_EXPERIMENTAL=1)")
+def test_packed_text_is_exact():
+    """Packing every caption to its EOT + 1 tokens (nothing after EOT can reach the pooled feature under
+    the causal mask) must give the same text features, loss and gradients as the full 77 positions."""
+    from construction_clip_b200 import towers
+    from construction_clip_b200.train import ClipTrainer
+    name, B = "ViT-B/32", 16
+    orc = oracle_model(name)
+    img, tok = _inputs(name, B, B, 60)
+    out = {}
+    for flag in (True, False):
+        towers.PACK_TEXT = flag
+        try:
+            m = device_model(name, orc).train()
+            with torch.no_grad():
+                ft = m.encode_text(tok.cuda())
+            tr = ClipTrainer(m)
+            loss = tr.forward_backward(img.cuda(), tok.cuda())
+            out[flag] = (ft.float(), loss.item(), {k: g.clone() for k, g in tr.grads.items()})
+        finally:
+            towers.PACK_TEXT = False
+    ft1, l1, g1 = out[True]
+    ft0, l0, g0 = out[False]
+    assert cosine_rows(ft1.cpu(), ft0.cpu()).min() > 0.99999
     assert abs(l1 - l0) <= 1e-4 * abs(l0)
     for k in g1:
         assert cosine(g1[k].cpu(), g0[k].cpu()) > 0.9999, k
