@@ -197,10 +197,6 @@ def test_attention_fwd_bwd(ops, B, S, H, causal):
     _close(dqkv, qr.grad, 4e-2, 4e-2, "attn bwd")
 
 
-EXPERIMENTAL = os.environ.get("B200CLIP_TEST_EXPERIMENTAL", "0") == "1"
-
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason="packed-text attention is experimental (set B200CLIP_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("lens,S,H,causal", [([77, 5, 33, 64, 1, 76, 17], 77, 8, True), ([50, 3, 20], 50, 2, False),
                                              ([9] * 40 + [70, 2, 31], 77, 8, True)])
 def test_attention_varlen(ops, lens, S, H, causal):

@@ -212,8 +212,6 @@ def test_pooled_last_block_is_exact():
         assert abs(g1[k].norm().item() / g0[k].norm().item() - 1) < 1e-2, k
 
 
-@pytest.mark.skipif(os.environ.get("B200CLIP_TEST_EXPERIMENTAL", "0") != "1",
-                    reason="packed text tower is experimental (set B200CLIP_TEST_EXPERIMENTAL=1)")
 def test_packed_text_is_exact():
     """Packing every caption to its EOT + 1 tokens (nothing after EOT can reach the pooled feature under
     the causal mask) must give the same text features, loss and gradients as the full 77 positions."""
