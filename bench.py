@@ -288,6 +288,38 @@ def run_ours(args):
     e2e_value = GLOBAL_BATCH * args.steps / (e2e_ms * 1e-3)
     _ = float(slot.item())
 
+    # ---------------- secondary, NOT the headline: the opt-in packed text tower ----------------
+    # (towers.PACK_TEXT: captions packed to EOT + 1 tokens -- same features / loss / gradients, see
+    # DESIGN.md §9.1.)  Single GPU only, eager launches, after every headline number has been taken; any
+    # failure here is recorded and cannot touch the figures above.
+    variants = {}
+    if world == 1 and os.environ.get("B200CLIP_BENCH_VARIANTS", "1") != "0":
+        try:
+            from construction_clip_b200 import towers as _T
+            was = _T.PACK_TEXT
+            _T.PACK_TEXT = True
+            try:
+                for i in range(2):
+                    trainer.step(*dev_batches[i % n_host])
+                torch.cuda.synchronize()
+                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                p0.record()
+                for i in range(args.steps):
+                    ploss = trainer.step(*dev_batches[i % n_host])
+                p1.record()
+                torch.cuda.synchronize()
+                pms = p0.elapsed_time(p1) / args.steps
+                variants["packed_text"] = {
+                    "value": GLOBAL_BATCH / (pms * 1e-3), "unit": "pairs/s", "ms_per_step": pms,
+                    "loss": float(ploss.item()),
+                    "note": "opt-in B200CLIP_PACK_TEXT=1: text tower on sum(caption lengths) rows instead of B x 77 "
+                            "(positions after EOT are dead under the causal mask: identical features, loss and "
+                            "gradients); eager launches, device-resident inputs; not the headline configuration"}
+            finally:
+                _T.PACK_TEXT = was
+        except Exception as exc:  # noqa: BLE001 -- a secondary figure must never break the contract line
+            variants["packed_text"] = {"error": repr(exc)[:300]}
+
     def shutdown():
         # Drop captured graphs (they hold NCCL kernels) BEFORE the communicator goes away, and leave
         # through os._exit: tearing down NCCL with live graph state has been seen to hang at exit.
@@ -335,6 +367,7 @@ def run_ours(args):
                 "ms_per_step": e2e_ms / args.steps},
         "gpu_launches": launches,
         "clocks": clocks,
+        "variants": variants,
         "roofline": {
             "bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
             "frac": gemm_tflops / peaks["bf16_sustained"], "traffic": traffic,
