@@ -1,5 +1,6 @@
 // Fused multi-head attention (head_dim 64) on tcgen05 tensor cores: single-tile kernels for
-// sequences <= 128 (forward + backward), a KV-streaming forward for longer sequences.
+// sequences <= 128 (forward + backward; also in a packed "varlen" form where every sample owns its own
+// number of rows), a KV-streaming forward and a two-pass blocked backward for longer sequences.
 // Replaces the core of nn.MultiheadAttention(need_weights=False, attn_mask=causal|None) inside
 // clip.model.ResidualAttentionBlock.attention: softmax(q k^T / sqrt(64) + mask) v
 // (vision tower: S = 50, full; text tower: S = 77, causal with upstream's mask that does NOT

@@ -6,6 +6,9 @@
 // `x @ visual.proj`, `x @ text_projection` and their autograd dgrad / wgrad
 // (reference call sites: CLIP/train.py:161 forward, CLIP/train.py:168 backward).
 //
+// Two kernels share the epilogue: gemm_pair_bf16_kernel (cta_group::2, one 256 x 256 tile per cluster of
+// two CTAs, the default for large problems) and gemm_bf16_kernel<BN> (one CTA, 128 x {256,192,128}
+// tiles); the launcher picks the shape with the smallest waves x tile-time makespan.
 // One persistent CTA per SM, 10 warps:
 //   warp 0     TMA producer (one elected lane)
 //   warp 1     TMEM allocator + MMA issuer (one elected lane)

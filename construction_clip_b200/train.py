@@ -11,9 +11,12 @@ becomes ``ClipTrainer.step(image, text)``:
     problem without writing the logits; row log-sum-exps are all-gathered so that every rank can
     form the EXACT gradient of the global loss w.r.t. its own embeddings (no gradient collective
     for activations),
-  * backward kernels fill a flat fp32 gradient buffer per tower, which is sum-all-reduced
-    (overlapped with the other tower's backward) and consumed by the fused AdamW kernel
-    (fp32 master weights, bf16 shadow = the tensors the forward kernels read).
+  * backward kernels fill a flat fp32 gradient buffer per tower; chunk by chunk, as soon as the
+    backward pass has finished the blocks a chunk covers, it is reduce-scattered, this rank's
+    1/N shard is updated by the fused AdamW kernel (fp32 master weights and moments sharded,
+    ZeRO-1 style) and the updated bf16 weights (= the tensors the forward kernels read) are
+    all-gathered in place -- on a side stream, under the rest of the backward.  With
+    ``shard_optimizer=False`` the gradients are sum-all-reduced in full instead.
 
 ``clip_contrastive_loss`` exposes the same fused, distributed loss as an autograd op for callers
 that keep their own optimiser (``loss.backward()`` then fills ``.grad`` of the local replica with
@@ -230,7 +233,7 @@ class ClipTrainer:
         self._hyper_slot = 0
 
     def enable_cuda_graph(self, on=True):
-        """Capture forward + loss + backward + all-reduce + AdamW once per input shape and replay it:
+        """Capture forward + loss + backward + gradient collectives + AdamW once per input shape and replay it:
         removes the ~500 launches / step of host work, which dominates when the per-GPU batch is
         small (strong scaling at 8 GPUs)."""
         self._use_graph = bool(on)
