@@ -136,13 +136,14 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, *, row_index=None, dr
 
 
 # ------------------------------------------------------------------------------------- attention
-def attn_fwd(qkv, B, S, H, causal, out=None, want_lse=False, cu=None):
-    """``cu`` (int32 [B+1]): packed rows -- sample b owns rows cu[b] .. cu[b+1]-1 (<= S) of ``qkv``."""
+def attn_fwd(qkv, B, S, H, causal, out=None, want_lse=False, cu=None, zero_fill=False):
+    """``cu`` (int32 [B+1]): packed rows -- sample b owns rows cu[b] .. cu[b+1]-1 (<= S) of ``qkv``;
+    ``zero_fill``: rows past cu[B] exist (static-shape packing) and must read as zeros."""
     if cu is not None:
         rows = qkv.shape[0]
         assert qkv.dtype == bf16 and qkv.is_contiguous() and qkv.shape[1] == 3 * H * 64 and cu.dtype == i32
         if out is None:
-            out = torch.empty((rows, H * 64), device=qkv.device, dtype=bf16)
+            out = (torch.zeros if zero_fill else torch.empty)((rows, H * 64), device=qkv.device, dtype=bf16)
         lse = torch.empty(rows * H, device=qkv.device, dtype=f32) if want_lse else None
         ctx, st = _ctx_stream(qkv)
         L.check(L.load().b200clip_attn_fwd_varlen(ctx, qkv.data_ptr(), out.data_ptr(), _ptr(lse), cu.data_ptr(), B, S, H,
@@ -158,12 +159,12 @@ def attn_fwd(qkv, B, S, H, causal, out=None, want_lse=False, cu=None):
     return (out, lse) if want_lse else out
 
 
-def attn_bwd(qkv, out, lse, dout, B, S, H, causal, dqkv=None, cu=None):
+def attn_bwd(qkv, out, lse, dout, B, S, H, causal, dqkv=None, cu=None, zero_fill=False):
     if cu is not None:
         rows = qkv.shape[0]
         assert qkv.is_contiguous() and dout.is_contiguous() and out.is_contiguous() and dout.shape == (rows, H * 64)
         if dqkv is None:
-            dqkv = torch.empty_like(qkv)
+            dqkv = torch.zeros_like(qkv) if zero_fill else torch.empty_like(qkv)
         ctx, st = _ctx_stream(qkv)
         L.check(L.load().b200clip_attn_bwd_varlen(ctx, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), dout.data_ptr(),
                                                   dqkv.data_ptr(), cu.data_ptr(), B, S, H, rows, 1 if causal else 0, st),

@@ -35,7 +35,13 @@ POOL_LAST_BLOCK = os.environ.get("B200CLIP_POOL_LAST_BLOCK", "1") != "0"
 # (tests/test_model_gpu.py::test_packed_text_is_exact), 47.6 vs 59.2 ms per 1024-pair step on one B200
 # with the bench's U{3..76} caption lengths.  Off by default: it needs a host sync per call (dynamic row
 # count), so the step is not captured into a CUDA graph, and it has only been validated on one GPU.
-PACK_TEXT = os.environ.get("B200CLIP_PACK_TEXT", "0") == "1"
+PACK_TEXT = os.environ.get("B200CLIP_PACK_TEXT", "0") in ("1", "2")
+# B200CLIP_PACK_TEXT=2 (NOT yet run on hardware): the same packing with STATIC shapes, so that the step can
+# be captured into CUDA graphs keyed by a row-count bucket.  The trainer sets PACK_ROWS_STATIC to the
+# bucket (>= the real row count) around its forward; the packed tensors then have exactly that many
+# rows, the surplus rows are all-zero (and stay finite / contribute nothing through every kernel).
+PACK_STATIC = os.environ.get("B200CLIP_PACK_TEXT", "0") == "2"
+PACK_ROWS_STATIC = None
 
 
 @dataclass
@@ -61,6 +67,7 @@ class BlockSaved:
 class TowerSaved:
     blocks: list = field(default_factory=list)
     extra: dict = field(default_factory=dict)
+    pad: bool = False  # static-shape packing: rows past cu[B] exist and must stay zero in the gradient stream
 
 
 def _blk(prefix: str, i: int) -> str:
@@ -87,10 +94,12 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None, 
         else:
             h1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"])
         qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
+        pad = cu is not None and PACK_ROWS_STATIC is not None  # surplus rows exist: the kernels never write them
         if save:
-            a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True, cu=cu)
+            saved.pad = pad
+            a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True, cu=cu, zero_fill=pad)
         else:
-            a, lse = O.attn_fwd(qkv, B, S, H, causal, cu=cu), None
+            a, lse = O.attn_fwd(qkv, B, S, H, causal, cu=cu, zero_fill=pad), None
         x2 = O.linear_fwd(a, W[p + "attn.out_proj.weight"], W[p + "attn.out_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x,
                           out_dtype=f32)
         if save:
@@ -111,9 +120,10 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None, 
 def _last_block_fwd(W, p, x, B, S, H, causal, saved, pool_rows, cu=None):
     save = saved is not None
     if save:
+        saved.pad = cu is not None and PACK_ROWS_STATIC is not None
         h1, mean1, rstd1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"], want_stats=True)
         qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
-        a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True, cu=cu)
+        a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True, cu=cu)   # only pooled rows of `a` are read below
     else:
         h1, mean1, rstd1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"]), None, None
         qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
@@ -168,7 +178,7 @@ def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved, on_
         if s.pool is not None:  # pooled last block: the gradients of every other token are exactly zero
             da = torch.zeros((s.a.shape[0], d_model), device=da.device, dtype=bf16).index_copy_(0, s.pool, da)
             dx2 = torch.zeros((s.a.shape[0], d_model), device=da.device, dtype=bf16).index_copy_(0, s.pool, dx2)
-        dqkv = O.attn_bwd(s.qkv, s.a, s.lse, da, B, S, H, causal, cu=cu)
+        dqkv = O.attn_bwd(s.qkv, s.a, s.lse, da, B, S, H, causal, cu=cu, zero_fill=saved.pad)
         O.colsum(dqkv[:, :d_model], gb[:d_model])
         O.linear_wgrad(dqkv, s.h1, G[p + "attn.in_proj_weight"])
         dh1 = O.linear_dgrad(dqkv, W[p + "attn.in_proj_weight"])
@@ -269,8 +279,14 @@ def text_fwd(W, cfg, text, save: bool):
         cu = torch.zeros(B + 1, device=ids.device, dtype=i32)
         cu[1:] = torch.cumsum(pos_eot + 1, 0)
         keep = torch.arange(S, device=ids.device, dtype=i32)[None, :] <= pos_eot[:, None]
-        rows_src = keep.reshape(-1).nonzero().squeeze(1)     # int64 [sum(lengths)], host sync (dynamic shape)
-        x = x.index_select(0, rows_src)
+        if PACK_ROWS_STATIC is None:
+            rows_src = keep.reshape(-1).nonzero().squeeze(1)  # int64 [sum(lengths)], host sync (dynamic shape)
+            x = x.index_select(0, rows_src)
+        else:  # static shapes: kept rows first (original order), then as many dropped rows as the bucket needs
+            order = torch.argsort((~keep).reshape(-1).to(torch.uint8), stable=True)
+            rows_src = order[:PACK_ROWS_STATIC].contiguous()
+            live = torch.arange(PACK_ROWS_STATIC, device=ids.device, dtype=i32) < cu[B]
+            x = x.index_select(0, rows_src) * live[:, None].to(x.dtype)   # surplus rows are all-zero
         eot = (cu[1:] - 1).contiguous()                       # the EOT rows of the packed layout
     x = blocks_fwd(W, "transformer.", cfg.transformer_layers, x, B, S, H, True, saved,
                    eot if POOL_LAST_BLOCK else None, cu)

@@ -239,6 +239,8 @@ class ClipTrainer:
         self._use_graph = bool(on)
         if not on:
             self._graph = None
+            if hasattr(self, "_packed_graphs"):
+                self._packed_graphs = {}
         return self
 
     def current_lr(self):
@@ -387,7 +389,7 @@ class ClipTrainer:
             out += [self.master[k], self.m[k], self.v[k], self.stores[k].w]
         return out
 
-    def _capture(self, image, text):
+    def _capture(self, image, text, pool=None):
         dev = self.device
         self._g_img = image.detach().clone()
         self._g_txt = text.detach().clone()
@@ -413,7 +415,7 @@ class ClipTrainer:
         self.step_count = count
         del backup
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with (torch.cuda.graph(graph) if pool is None else torch.cuda.graph(graph, pool=pool)):
             self._hyper_live = True
             loss = self.forward_backward(self._g_img, self._g_txt, fused_update=True)
             self.optimizer_step(hyper=self._hyper, towers=not self.sharded, _count=False)
@@ -440,6 +442,44 @@ class ClipTrainer:
         self._graph.replay()
         self.last_correct = self._g_correct[0]
         return self._g_loss[0]
+
+    # -- packed text tower + CUDA graphs (B200CLIP_PACK_TEXT=2; NOT yet run on hardware) ----------------------
+    def _packed_rows(self, text):
+        """Rows of the packed text tower for this batch = sum over captions of (EOT position + 1).
+        step_from_host leaves the figure computed from the HOST tokens; device tokens cost one sync."""
+        hint, self._rows_hint = getattr(self, "_rows_hint", None), None
+        return hint if hint is not None else int((text.argmax(-1).long() + 1).sum().item())
+
+    def _packed_graph_step(self, image, text, bucket_rows=2048):
+        """One CUDA graph per row-count bucket (all buckets share one memory pool; they never run
+        concurrently).  Inside a graph the packed tensors have exactly `bucket` rows; the surplus rows
+        are zero and inert (towers.PACK_ROWS_STATIC)."""
+        B, S = text.shape
+        rows = self._packed_rows(text)
+        bucket = min(B * S, -(-rows // bucket_rows) * bucket_rows)
+        key = (tuple(image.shape), image.dtype, tuple(text.shape), text.dtype, bucket)
+        if not hasattr(self, "_packed_graphs"):
+            self._packed_graphs, self._graph_pool = {}, torch.cuda.graph_pool_handle()
+        entry = self._packed_graphs.get(key)
+        if entry is None:
+            keep = (self._graph, self._graph_key, getattr(self, "_g_img", None), getattr(self, "_g_txt", None),
+                    getattr(self, "_g_loss", None), getattr(self, "_g_correct", None))
+            T.PACK_ROWS_STATIC = bucket
+            try:
+                self._capture(image, text, pool=self._graph_pool)
+                entry = (self._graph, self._g_img, self._g_txt, self._g_loss, self._g_correct)
+            finally:
+                T.PACK_ROWS_STATIC = None
+                (self._graph, self._graph_key, self._g_img, self._g_txt, self._g_loss, self._g_correct) = keep
+            self._packed_graphs[key] = entry
+        graph, g_img, g_txt, g_loss, g_correct = entry
+        g_img.copy_(image, non_blocking=True)
+        g_txt.copy_(text, non_blocking=True)
+        self.step_count += 1
+        self._push_hyper()
+        graph.replay()
+        self.last_correct = g_correct[0]
+        return g_loss[0]
 
     def write_back(self):
         """Copies the fp32 master weights into parameters that are not views of the bf16 shadow
@@ -488,6 +528,8 @@ class ClipTrainer:
         cur.wait_event(ev)
         img_d.record_stream(cur)
         txt_d.record_stream(cur)
+        if T.PACK_STATIC:  # row count of the packed text tower from the host copy of the tokens: no device sync
+            self._rows_hint = int((text_host.argmax(-1).long() + 1).sum())
         # enqueue this step's GPU work FIRST: cudaMemcpyAsync of a large pinned batch can hold the host
         # thread for about the DMA time (measured 1.9 ms for 77 MB, more when copies queue up), and that
         # must not delay the launch of the step the GPU is waiting for
@@ -501,8 +543,11 @@ class ClipTrainer:
     def step(self, image, text):
         """One optimisation step on this rank's slice (image [Bl,3,R,R], text [Bl,77]) of the
         global batch; returns the global mean loss as a device tensor (no host sync)."""
-        if self._use_graph and not T.PACK_TEXT:  # packed text has a data-dependent row count: eager launches
+        if self._use_graph and not T.PACK_TEXT:
             return self._graph_step(image, text)
+        if self._use_graph and T.PACK_STATIC:   # packed text with static (bucketed) shapes: one graph per bucket
+            return self._packed_graph_step(image, text)
+        # (packed text, B200CLIP_PACK_TEXT=1: data-dependent row count -> eager launches)
         self.step_count += 1
         loss = self.forward_backward(image, text, fused_update=True)
         self.optimizer_step(towers=not self.sharded, _count=False)
