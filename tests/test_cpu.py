@@ -322,3 +322,47 @@ def test_optimizer_chunk_plan(name):
                     assert tag <= layer, (n, tag)      # reduced only after block `tag` <= this block is done
                 elif not n.startswith(head):
                     assert tag == -1, (n, tag)         # embeddings, conv1, ln_pre: final at the very end
+
+
+def test_positions_after_eot_are_dead_in_the_oracle():
+    """The claim behind the packed text tower (towers.PACK_TEXT) and the pooled last block, proven on the
+    fp32 CPU oracle: under upstream's causal mask (a) the text feature of a caption does not depend on
+    anything after its EOT token -- truncating the caption at EOT, or replacing the tail by other ids,
+    gives the same feature -- and (b) the loss gradient w.r.t. the token/positional embeddings of those
+    positions is exactly zero."""
+    from oracle import clip_oracle as O
+    torch.manual_seed(0)
+    orc = O.build("tiny", seed=SEED, jitter=0.05)
+    tok = O.synth_tokens(6, seed=3, min_len=3, max_len=20)
+    eot = tok.argmax(-1)
+    full = orc.encode_text(tok)
+    # (a1) garbage after EOT (ids below EOT so that arg-max pooling still finds the same position)
+    junk = tok.clone()
+    for b in range(tok.shape[0]):
+        junk[b, int(eot[b]) + 1:] = torch.randint(1, O.SOT, (tok.shape[1] - int(eot[b]) - 1,))
+    assert torch.allclose(orc.encode_text(junk), full, atol=1e-6, rtol=1e-6)
+    # (a2) a caption alone, cut at EOT + 1 tokens, through the same blocks with an L x L causal mask
+    for b in range(tok.shape[0]):
+        L = int(eot[b]) + 1
+        x = orc.token_embedding(tok[b:b + 1, :L]) + orc.positional_embedding[:L]
+        x = x.permute(1, 0, 2)
+        mask = torch.full((L, L), float("-inf")).triu_(1)
+        for blk in orc.transformer.resblocks:
+            saved = blk.attn_mask
+            blk.attn_mask = mask
+            try:
+                x = blk(x)
+            finally:
+                blk.attn_mask = saved
+        x = orc.ln_final(x.permute(1, 0, 2))
+        feat = x[0, L - 1] @ orc.text_projection
+        assert torch.allclose(feat, full[b], atol=1e-5, rtol=1e-5), b
+    # (b) zero gradient into the dead positions
+    emb = (orc.token_embedding(tok) + orc.positional_embedding).detach().requires_grad_(True)
+    x = orc.transformer(emb.permute(1, 0, 2)).permute(1, 0, 2)
+    x = orc.ln_final(x)
+    f = x[torch.arange(tok.shape[0]), eot] @ orc.text_projection
+    f.square().sum().backward()
+    for b in range(tok.shape[0]):
+        assert emb.grad[b, int(eot[b]) + 1:].abs().max().item() == 0.0
+        assert emb.grad[b, :int(eot[b]) + 1].abs().max().item() > 0.0
