@@ -366,3 +366,29 @@ def test_positions_after_eot_are_dead_in_the_oracle():
     for b in range(tok.shape[0]):
         assert emb.grad[b, int(eot[b]) + 1:].abs().max().item() == 0.0
         assert emb.grad[b, :int(eot[b]) + 1].abs().max().item() > 0.0
+
+
+@pytest.mark.parametrize("causal", [False, True])
+def test_in_proj_bias_gradient_identities(causal):
+    """The identities towers.blocks_bwd uses to get the in_proj_bias gradient without re-reading dqkv:
+    the K third is zero (a key bias shifts every score of a row equally) and the V third equals the
+    column sum of the gradient w.r.t. the attention output that feeds out_proj (softmax rows sum to 1)."""
+    torch.manual_seed(1)
+    S, B, d, H = 9, 3, 64, 2
+    dh = d // H
+    f64 = torch.float64
+    w_in = torch.randn(3 * d, d, dtype=f64) * 0.2
+    b_in = torch.randn(3 * d, dtype=f64, requires_grad=True)
+    x = torch.randn(B, S, d, dtype=f64)
+    q, k, v = (x @ w_in.t() + b_in).view(B, S, 3, H, dh).permute(2, 0, 3, 1, 4)
+    s_ = q @ k.transpose(-1, -2) / dh ** 0.5
+    if causal:
+        s_ = s_ + torch.full((S, S), float("-inf"), dtype=f64).triu_(1)
+    a = (torch.softmax(s_, -1) @ v).permute(0, 2, 1, 3).reshape(B, S, d)   # what out_proj consumes
+    a.retain_grad()
+    out = a @ (torch.randn(d, d, dtype=f64) * 0.2).t()
+    (out * torch.randn_like(out)).sum().backward()
+    gq, gk, gv = b_in.grad.split(d)
+    assert gk.abs().max().item() < 1e-12 * max(1.0, gq.abs().max().item())
+    assert torch.allclose(gv, a.grad.reshape(-1, d).sum(0), atol=1e-10, rtol=1e-10)
+    assert gq.abs().max().item() > 1e-6
