@@ -24,10 +24,13 @@ call sites:
 * un-normalised ``encode_image`` output used as the prefix           parse_coco.py:43
 
 PARITY PINNING: the reference holds no tests, golden vectors or fixtures for this
-path ("parity unpinned" by the reference itself).  The restatement is pinned
-instead against an independent implementation of the same published model,
-HuggingFace ``transformers`` ``CLIPModel`` (``tests/test_oracle.py``), and the
-fixtures in ``tests/golden/`` are generated from it by ``oracle/gen_golden.py``.
+path ("parity unpinned" by the reference itself, and upstream ``clip`` cannot be imported
+here).  The restatement is pinned instead against the one independent implementation
+of the same published model that is importable offline, HuggingFace ``transformers``
+``CLIPModel``: ``oracle/gen_golden.py`` computes every stored output (features, logits,
+loss, the gradient norm of all parameter tensors and a few full gradients) with
+``CLIPModel`` -- this module only supplies the seeded weights and inputs -- and
+``tests/test_cpu.py`` checks this oracle against those fixtures and against HF live.
 """
 from __future__ import annotations
 
