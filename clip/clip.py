@@ -6,7 +6,13 @@ Differences from upstream, all forced by the environment and documented in DESIG
     file names; if absent the model is RANDOM-INITIALISED with upstream's scheme and a warning is
     printed (set CLIP_B200_REQUIRE_WEIGHTS=1 to make that an error).  The reference scripts
     load their own fine-tuned state dict right after `clip.load` anyway.
-  * on CUDA the model computes in bf16 (upstream: fp16); there is no CPU execution path --
+  * on CUDA the kernels compute in bf16 with fp32 accumulation (upstream: fp16), reading a bf16 shadow of
+    the weights, while the nn.Parameters returned by `clip.load` stay **fp32**: the reference fine-tunes
+    with `AdamW(model.parameters(), lr=1e-5)` (CLIP/train.py:143), and an update of 1e-5 is below half a
+    bf16 ulp for almost every weight -- bf16 parameters would silently not train.  The shadow is
+    refreshed (one multi-tensor cast) whenever a parameter's version counter moves.
+    `clip.model.convert_weights(model)` still gives bf16 parameters that alias the shadow (zero copy,
+    inference / ClipTrainer with its own fp32 master weights).  There is no CPU execution path --
     `device="cpu"` builds the module (state_dict round trips work) but calling it raises.
   * ViT models only (BASELINE config 4: "RN-free"); `jit=True` is not supported.
 """
@@ -88,11 +94,7 @@ def load(name: str, device: Union[str, torch.device] = "cuda" if torch.cuda.is_a
         model = CLIP(CONFIGS[name])
 
     device = torch.device(device)
-    if device.type == "cuda":
-        from .model import convert_weights
-        model = convert_weights(model.to(device))
-    else:
-        model = model.float()
+    model = model.float().to(device)   # fp32 master parameters on either device (see the module docstring)
     model.eval()
     return model, _transform(model.visual.input_resolution)
 

@@ -306,7 +306,11 @@ __global__ void cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, f
 }
 
 // ------------------------------------------------------------------------------------------------
-// AdamW (decoupled weight decay), fp32 master weights + bf16 shadow copy
+// AdamW as the reference's optimiser computes it -- transformers.AdamW (CLIP/train.py:143, correct_bias=True):
+//   m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= lr sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps) ; p -= lr wd p
+// Unlike torch.optim.AdamW, eps is added to the UN-corrected sqrt(v) (an effective eps 1/sqrt(1-b2^t) times larger,
+// ~32x at t = 1) and the decoupled decay is applied after the update with the plain lr.
+// fp32 master weights + bf16 shadow copy.
 __global__ void __launch_bounds__(256)
 adamw_kernel(float* __restrict__ master, __nv_bfloat16* __restrict__ param, const float* __restrict__ grad,
              float* __restrict__ m, float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
@@ -316,6 +320,7 @@ adamw_kernel(float* __restrict__ master, __nv_bfloat16* __restrict__ param, cons
         bc1 = __ldg(hyper + 1);
         bc2 = __ldg(hyper + 2);
     }
+    const float step_size = lr * sqrtf(bc2) / bc1;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
         const float g = grad[i] * grad_scale;
@@ -324,8 +329,8 @@ adamw_kernel(float* __restrict__ master, __nv_bfloat16* __restrict__ param, cons
         const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
         m[i] = mi;
         v[i] = vi;
+        p -= step_size * mi / (sqrtf(vi) + eps);
         p -= lr * wd * p;
-        p -= lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
         master[i] = p;
         if (param != nullptr) param[i] = __float2bfloat16_rn(p);
     }

@@ -166,25 +166,61 @@ class ParamStore:
             dst.zero_()
             dst[:, :p[0].numel()].copy_(p.detach().reshape(p.shape[0], -1))
 
+    def _copy_in_many(self, items):
+        """Refresh many shadow entries with ONE multi-tensor copy (an optimizer.step() on fp32 parameters
+        touches all ~150 tensors of a tower; one launch per tensor would cost more than the forward's LayerNorms)."""
+        same = [(self.W[n], p.detach()) for n, p in items if self.W[n].shape == p.shape]
+        if len(same) > 1 and hasattr(torch, "_foreach_copy_"):
+            torch._foreach_copy_([d for d, _ in same], [q for _, q in same])
+        else:
+            for d, q in same:
+                d.copy_(q)
+        for n, p in items:
+            if self.W[n].shape != p.shape:
+                self._copy_in(n, p)
+
     def link(self):
         """(Re-)point bf16 parameters at the shadow so kernels and optimiser share storage."""
         with torch.no_grad():
+            self._copy_in_many([(name, p) for name, p, _, _ in self.entries])
             for name, p, o, s in self.entries:
-                self._copy_in(name, p)
                 if p.dtype == bf16 and p.device == self.w.device and math.prod(s) == p.numel():
                     p.data = self.W[name].view(p.shape)
                 self._seen[name] = (p.data_ptr(), p._version)
 
     def sync(self):
         """Refresh shadow entries whose parameter is not a view of the shadow and has changed."""
+        stale = []
+        for name, p, o, s in self.entries:
+            ptr = p.data_ptr()
+            if ptr == self.W[name].data_ptr() and p.dtype == bf16:
+                continue
+            if self._seen.get(name) != (ptr, p._version):
+                stale.append((name, p))
+                self._seen[name] = (ptr, p._version)
+        if stale:
+            with torch.no_grad():
+                self._copy_in_many(stale)
+
+    def unlinked(self):
+        """Entries whose nn.Parameter is NOT a zero-copy view of the shadow (fp32 / fp16 parameters, the
+        zero-padded conv1.weight of ViT-L/14): a trainer that updates the shadow must write them back."""
+        return [(name, p, o, s) for name, p, o, s in self.entries
+                if not (p.data_ptr() == self.W[name].data_ptr() and p.dtype == bf16)]
+
+    def master_f32(self):
+        """Flat fp32 copy of the tower's weights for an optimiser: taken from the nn.Parameters themselves
+        when they carry more precision than the bf16 shadow (fp32 parameters, what clip.load returns)."""
+        out = self.w.float()
         with torch.no_grad():
             for name, p, o, s in self.entries:
-                ptr = p.data_ptr()
-                if ptr == self.W[name].data_ptr() and p.dtype == bf16:
-                    continue
-                if self._seen.get(name) != (ptr, p._version):
-                    self._copy_in(name, p)
-                    self._seen[name] = (ptr, p._version)
+                if p.dtype == f32 and p.device == self.w.device:
+                    dst = out[o:o + math.prod(s)].view(s)
+                    if tuple(s) == tuple(p.shape):
+                        dst.copy_(p.detach())
+                    else:
+                        dst[:, :p[0].numel()].copy_(p.detach().reshape(p.shape[0], -1))
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -286,6 +322,7 @@ class CLIP(nn.Module):
         self.text_projection = nn.Parameter(torch.empty(cfg.transformer_width, cfg.embed_dim))
         self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
         self._stores = {}
+        self._trainer = None          # weakref to the ClipTrainer that owns the master weights, if any
         self.fp32_check_mode = False  # see set_fp32_check_mode
         self.initialize_parameters()
 
@@ -326,6 +363,16 @@ class CLIP(nn.Module):
             st = ParamStore(self._tower_named_params(which), device, special)
             self._stores[which] = st
         return st
+
+    def state_dict(self, *a, **k):
+        """A ClipTrainer updates flat master weights + the bf16 shadow; parameters that are not views of the
+        shadow (fp32 parameters, padded conv1.weight) are refreshed here so that the checkpoints of
+        CLIP/train.py:210-216 (`torch.save(model.state_dict())`) always hold the trained weights.  With a
+        sharded optimiser this gathers the master shards: call it on every rank."""
+        tr = self._trainer() if getattr(self, "_trainer", None) is not None else None
+        if tr is not None and tr.dirty:
+            tr.write_back()
+        return super().state_dict(*a, **k)
 
     def _apply(self, fn, *a, **k):  # .to() / .float() / .half() invalidate the zero-copy links
         out = super()._apply(fn, *a, **k)

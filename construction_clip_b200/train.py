@@ -212,8 +212,9 @@ class ClipTrainer:
             for j, c in enumerate(chunks):
                 if c[4] >= 0:
                     self.chunk_ready[k].setdefault(c[4], []).append(j)
-            self.master[k] = torch.cat([st.w[a + self.rank * n * int(self.sharded):][:n].float()
-                                        for a, b, _, n, _ in chunks])
+            full = st.master_f32()  # fp32 parameters (clip.load) keep their precision; bf16 ones are upcast
+            self.master[k] = torch.cat([full[a + self.rank * n * int(self.sharded):][:n] for a, b, _, n, _ in chunks])
+            del full
             self.m[k] = torch.zeros(moff, device=self.device, dtype=f32)
             self.v[k] = torch.zeros(moff, device=self.device, dtype=f32)
         self.G = {k: self.stores[k].grad_views(self.grads[k]) for k in self.stores}
@@ -231,6 +232,14 @@ class ClipTrainer:
         self._hyper = torch.zeros(3, device=self.device, dtype=f32)
         self._hyper_host = torch.zeros((64, 3), dtype=f32).pin_memory() if self.device.type == "cuda" else None
         self._hyper_slot = 0
+        self._hyper_events = [None] * 64
+        # Parameters that are not views of the bf16 shadow go stale when this trainer updates the weights;
+        # CLIP.state_dict() calls write_back() while `dirty` (CLIP/train.py:210-216 saves model.state_dict()).
+        import weakref
+        self._has_unlinked = any(st.unlinked() for st in self.stores.values())
+        self.dirty = False
+        self._grads_reduced = False
+        model._trainer = weakref.ref(self)
 
     def enable_cuda_graph(self, on=True):
         """Capture forward + loss + backward + gradient collectives + AdamW once per input shape and replay it:
@@ -265,6 +274,7 @@ class ClipTrainer:
         dev = self.device
         for k in self.grads:
             self.grads[k].zero_()
+        self._grads_reduced = False
         Wv, Wt = self.stores["visual"].W, self.stores["text"].W
         two = self.two_streams and dev.type == "cuda"
         main = torch.cuda.current_stream(dev)
@@ -306,6 +316,7 @@ class ClipTrainer:
                             s_tower.wait_stream(self._comm_streams[k])
                     else:
                         work.append(dist.all_reduce(self.grads[k], group=self.group, async_op=True))
+                        self._grads_reduced = True
         if two:
             main.wait_stream(sv)
             main.wait_stream(stt)
@@ -322,10 +333,11 @@ class ClipTrainer:
         return dict(lr=self.current_lr() if hyper is None else 0.0, beta1=b1, beta2=b2, eps=self.eps,
                     weight_decay=self.wd, grad_scale=1.0, step=self.step_count if hyper is None else 0, hyper=hyper)
 
-    def _sharded_update(self, k, hyper, ready=None, only=None):
+    def _sharded_update(self, k, hyper, ready=None, only=None, reduced=False):
         """reduce-scatter(grad) -> AdamW on the local shard -> all-gather(bf16 weights) on the current
         stream, for the chunks of tower ``k`` selected by ``only`` (indices) / ``ready`` (their
-        ready-layer tag) -- all of them by default."""
+        ready-layer tag) -- all of them by default.  ``reduced``: the flat gradients already hold the
+        sum over ranks (forward_backward all-reduced them), so this rank's slice is used as it is."""
         st = self.stores[k]
         g = self.grads[k]
         for j, (a, b, moff, n, tag) in enumerate(self.chunks[k]):
@@ -333,7 +345,8 @@ class ClipTrainer:
                 continue
             lo = a + self.rank * n
             grp = self._tower_group[k]
-            dist.reduce_scatter_tensor(g[lo:lo + n], g[a:b], group=grp)
+            if not reduced:
+                dist.reduce_scatter_tensor(g[lo:lo + n], g[a:b], group=grp)
             O.adamw(self.master[k][moff:moff + n], st.w[lo:lo + n], g[lo:lo + n], self.m[k][moff:moff + n],
                     self.v[k][moff:moff + n], **self._adam_args(hyper))
             dist.all_gather_into_tensor(st.w[a:b], st.w[lo:lo + n], group=grp)
@@ -358,15 +371,18 @@ class ClipTrainer:
 
     def optimizer_step(self, hyper=None, towers=True, _count=True):
         """AdamW on both flat buffers + logit_scale.  ``hyper`` (device float[3]) carries lr and the
-        bias corrections when the step is replayed from a CUDA graph.  With a sharded optimiser the
-        gradients in ``self.grads`` must NOT have been all-reduced yet (``step`` fuses the tower
-        updates into ``forward_backward``; this entry point then only handles logit_scale)."""
+        bias corrections when the step is replayed from a CUDA graph.  Works after either form of
+        ``forward_backward``: with a sharded optimiser the gradients are reduce-scattered here unless
+        ``forward_backward(fused_update=False)`` has already sum-all-reduced them (then each rank
+        just takes its slice); ``step`` fuses the tower updates into ``forward_backward`` and calls
+        this with ``towers=False`` for logit_scale only."""
         if _count and hyper is None:
             self.step_count += 1
+        self.dirty = self._has_unlinked
         if towers:
             for k, st in self.stores.items():
                 if self.sharded:
-                    self._sharded_update(k, hyper)
+                    self._sharded_update(k, hyper, reduced=self._grads_reduced)
                 else:
                     O.adamw(self.master[k], st.w, self.grads[k], self.m[k], self.v[k], **self._adam_args(hyper))
         O.adamw(self.ls_master, None, self.d_ls, self.ls_m, self.ls_v, **self._adam_args(hyper))
@@ -376,11 +392,17 @@ class ClipTrainer:
     # ------------------------------------------------------------------------------ CUDA graph
     def _push_hyper(self):
         b1, b2 = self.betas
+        ev = self._hyper_events[self._hyper_slot]
+        if ev is not None:   # the copy that last read this pinned slot (64 steps ago) must have executed
+            ev.synchronize()
         row = self._hyper_host[self._hyper_slot]
         row[0] = self.current_lr()
         row[1] = 1.0 - b1 ** self.step_count
         row[2] = 1.0 - b2 ** self.step_count
         self._hyper.copy_(row, non_blocking=True)
+        if self._hyper_events[self._hyper_slot] is None:
+            self._hyper_events[self._hyper_slot] = torch.cuda.Event()
+        self._hyper_events[self._hyper_slot].record()
         self._hyper_slot = (self._hyper_slot + 1) % 64
 
     def _state_tensors(self):
@@ -398,30 +420,44 @@ class ClipTrainer:
         count = self.step_count
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                self.step_count += 1
-                self._push_hyper()
+        try:  # whatever happens (a failed warm-up or capture falls back to eager), the optimiser state is restored
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    self.step_count += 1
+                    self._push_hyper()
+                    self._hyper_live = True
+                    self.forward_backward(self._g_img, self._g_txt, fused_update=True)
+                    self.optimizer_step(hyper=self._hyper, towers=not self.sharded, _count=False)
+                    self._hyper_live = False
+            torch.cuda.current_stream(dev).wait_stream(side)
+            torch.cuda.synchronize(dev)
+        finally:
+            self._hyper_live = False
+            with torch.no_grad():
+                for t, b in zip(self._state_tensors(), backup):
+                    t.copy_(b)
+                self.model.logit_scale.copy_(self.ls_master.reshape(()))
+            self.step_count = count
+            del backup
+        backup = [t.clone() for t in self._state_tensors()]   # a capture that dies half-way may have run nothing,
+        graph = torch.cuda.CUDAGraph()                         # but restore anyway: capture must be side-effect free
+        try:
+            with (torch.cuda.graph(graph) if pool is None else torch.cuda.graph(graph, pool=pool)):
                 self._hyper_live = True
-                self.forward_backward(self._g_img, self._g_txt, fused_update=True)
+                loss = self.forward_backward(self._g_img, self._g_txt, fused_update=True)
                 self.optimizer_step(hyper=self._hyper, towers=not self.sharded, _count=False)
                 self._hyper_live = False
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        with torch.no_grad():
-            for t, b in zip(self._state_tensors(), backup):
-                t.copy_(b)
-            self.model.logit_scale.copy_(self.ls_master.reshape(()))
-        self.step_count = count
-        del backup
-        graph = torch.cuda.CUDAGraph()
-        with (torch.cuda.graph(graph) if pool is None else torch.cuda.graph(graph, pool=pool)):
-            self._hyper_live = True
-            loss = self.forward_backward(self._g_img, self._g_txt, fused_update=True)
-            self.optimizer_step(hyper=self._hyper, towers=not self.sharded, _count=False)
+                self._g_loss = loss.reshape(1).clone()
+                self._g_correct = self.last_correct.reshape(1).clone()
+        except Exception:
             self._hyper_live = False
-            self._g_loss = loss.reshape(1).clone()
-            self._g_correct = self.last_correct.reshape(1).clone()
+            torch.cuda.synchronize(dev)
+            with torch.no_grad():
+                for t, b in zip(self._state_tensors(), backup):
+                    t.copy_(b)
+            raise
+        finally:
+            del backup
         self._graph = graph
         self._graph_key = (tuple(image.shape), image.dtype, tuple(text.shape), text.dtype)
 
@@ -486,18 +522,22 @@ class ClipTrainer:
         (e.g. after ``model.float()``); linked bf16 parameters are already up to date."""
         with torch.no_grad():
             for k, st in self.stores.items():
+                todo = st.unlinked()
+                if not todo:
+                    continue
                 full = self.master[k]
-                if self.sharded:
+                if self.sharded:   # collective: every rank must get here (CLIP.state_dict() on all ranks)
                     full = torch.empty(st.total, device=self.device, dtype=f32)
                     for a, b, moff, n, _ in self.chunks[k]:
                         dist.all_gather_into_tensor(full[a:b], self.master[k][moff:moff + n], group=self.group)
-                for name, p, o, s in st.entries:
-                    if p.data_ptr() != st.W[name].data_ptr():
-                        n = math.prod(s)
-                        src = full[o:o + n].view(s)
-                        if tuple(s) != tuple(p.shape):
-                            src = src[:, :math.prod(p.shape[1:])]
-                        p.copy_(src.reshape(p.shape))
+                for name, p, o, s in todo:
+                    n = math.prod(s)
+                    src = full[o:o + n].view(s)
+                    if tuple(s) != tuple(p.shape):
+                        src = src[:, :math.prod(p.shape[1:])]
+                    p.copy_(src.reshape(p.shape))
+                    st._seen[name] = (p.data_ptr(), p._version)   # the shadow already holds these values
+        self.dirty = False
 
     # ---------------------------------------------------------------------------- host-fed steps
     def step_from_host(self, image_host, text_host, next_batch=None):
@@ -543,6 +583,7 @@ class ClipTrainer:
     def step(self, image, text):
         """One optimisation step on this rank's slice (image [Bl,3,R,R], text [Bl,77]) of the
         global batch; returns the global mean loss as a device tensor (no host sync)."""
+        self.dirty = self._has_unlinked
         if self._use_graph and not T.PACK_TEXT:
             return self._graph_step(image, text)
         if self._use_graph and T.PACK_STATIC:   # packed text with static (bucketed) shapes: one graph per bucket

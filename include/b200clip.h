@@ -234,7 +234,9 @@ int b200clip_check_im2col_f32(b200clip_ctx* ctx, const float* image, float* cols
                               int64_t patch, void* stream);
 
 /* ---- AdamW step (CLIP/train.py:143,169) on flat buffers: fp32 master weights, bf16 shadow -------
- * p -= lr * (m_hat / (sqrt(v_hat) + eps) + wd * p);  grad fp32 (multiplied by grad_scale).
+ * The update is transformers.AdamW's (the optimiser the reference constructs, correct_bias=True):
+ *   p -= lr * sqrt(1 - beta2^step) / (1 - beta1^step) * m / (sqrt(v) + eps);  then  p -= lr * wd * p
+ * (eps is added to the un-corrected sqrt(v); torch.optim.AdamW differs).  grad fp32 (multiplied by grad_scale).
  * hyper_dev: optional DEVICE float[3] = {lr, 1 - beta1^step, 1 - beta2^step}; when non-NULL it overrides
  * `lr` / `step`, so that a captured CUDA graph of the step can be replayed with a changing schedule. */
 int b200clip_adamw(b200clip_ctx* ctx, float* master, void* param_bf16, const float* grad, float* m, float* v,

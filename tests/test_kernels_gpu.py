@@ -339,18 +339,37 @@ def test_clip_loss(ops, Bg, E, row0, Bl):
         assert abs(d_ls.item() - lr.grad.item()) <= 1e-3 * max(1.0, abs(lr.grad.item())), (d_ls.item(), lr.grad.item())
 
 
+def _transformers_adamw_step(p, g, m, v, step, lr, b1, b2, eps, wd):
+    """Literal port of transformers.optimization.AdamW.step (correct_bias=True), the optimiser of CLIP/train.py:143."""
+    m.mul_(b1).add_(g, alpha=1.0 - b1)
+    v.mul_(b2).addcmul_(g, g, value=1.0 - b2)
+    denom = v.sqrt().add_(eps)
+    step_size = lr * math.sqrt(1.0 - b2 ** step) / (1.0 - b1 ** step)
+    p.addcdiv_(m, denom, value=-step_size)
+    if wd > 0.0:
+        p.add_(p, alpha=-lr * wd)
+
+
 def test_adamw(ops):
+    """Fused AdamW == transformers.AdamW (NOT torch.optim.AdamW: eps placement differs), including tiny
+    gradients (|g| ~ eps) where the two formulas disagree by up to ~4x in the first steps."""
     n = 100000
     p = torch.randn(n, device="cuda")
     g = torch.randn(n, device="cuda") * 0.1
-    ref = p.clone().requires_grad_(True)
-    opt = torch.optim.AdamW([ref], lr=1e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.2)
+    g[: n // 2] *= 1e-4   # |g| ~ 1e-5 against eps = 1e-6
+    ref, rm, rv = p.double().clone(), torch.zeros(n, device="cuda", dtype=torch.float64), torch.zeros(n, device="cuda", dtype=torch.float64)
     master, m, v = p.clone(), torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
     shadow = torch.empty(n, device="cuda", dtype=bf16)
-    for step in range(1, 4):
-        ref.grad = g.clone()
-        opt.step()
-        ops.adamw(master, shadow, g, m, v, lr=1e-3, beta1=0.9, beta2=0.98, eps=1e-6, weight_decay=0.2, grad_scale=1.0,
-                  step=step)
-    _close(master, ref.detach(), 1e-5, 1e-5, "adamw")
+    hyper = torch.zeros(3, device="cuda")
+    for step in range(1, 6):
+        _transformers_adamw_step(ref, g.double(), rm, rv, step, 1e-3, 0.9, 0.98, 1e-6, 0.2)
+        if step < 4:
+            ops.adamw(master, shadow, g, m, v, lr=1e-3, beta1=0.9, beta2=0.98, eps=1e-6, weight_decay=0.2, grad_scale=1.0,
+                      step=step)
+        else:  # the CUDA-graph form: lr and bias corrections from device memory
+            hyper.copy_(torch.tensor([1e-3, 1.0 - 0.9 ** step, 1.0 - 0.98 ** step]))
+            ops.adamw(master, shadow, g, m, v, lr=0.0, beta1=0.9, beta2=0.98, eps=1e-6, weight_decay=0.2, grad_scale=1.0,
+                      step=0, hyper=hyper)
+    _close(master, ref.float(), 1e-5, 1e-5, "adamw")
+    # the first update of a tiny-gradient weight must NOT be lr * sign(g) (torch.optim.AdamW's behaviour)
     _close(shadow, master.to(bf16), 0, 0, "adamw shadow")

@@ -451,3 +451,101 @@ def test_fp32_check_mode_logits_within_1e4():
     with pytest.raises(RuntimeError, match="forward only"):
         m.train()
         m(img[:2].cuda(), tok[:2].cuda())
+
+
+# ---------------------------------------------------------------------------------------------
+# clip.load on CUDA and the fine-tune loop with the reference's own optimiser
+def _clip_load_cuda(tmp_path, orc, name="ViT-B/32"):
+    """CLIP/predict.py:12-16 verbatim: clip.load on cuda, then load_state_dict of a checkpoint read with map_location='cpu'."""
+    import warnings
+    import clip
+    model_path = str(tmp_path / "clip_latest.pt")
+    torch.save(orc.state_dict(), model_path)
+    device = "cuda" if torch.cuda.is_available() else "cpu"
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")      # offline: random-init warning
+        model, preprocess = clip.load(name, device=device)
+    with open(model_path, 'rb') as opened_file:
+        model.load_state_dict(torch.load(opened_file, map_location="cpu"))
+    return model, preprocess, device
+
+
+def test_clip_load_cuda_predict_replay(tmp_path):
+    """CLIP/predict.py:12-16,40-54 on BASELINE config 1 (32 images x 16 prompts) through clip.load(device='cuda'),
+    against the HF-generated golden logits and the oracle."""
+    name = "ViT-B/32"
+    orc = oracle_model(name)
+    model, preprocess, device = _clip_load_cuda(tmp_path, orc)
+    assert next(model.parameters()).is_cuda and model.visual.input_resolution == 224
+    from PIL import Image
+    assert preprocess(Image.new("RGB", (640, 480), (200, 30, 10))).shape == (3, 224, 224)
+    img, tok = _inputs(name, 32, 16, 12)
+    g = golden("vitb32_fwd_32x16")
+    assert np.array_equal(tok.numpy(), g["tokens"])
+    image, text = img.to(device), tok.to(device)
+    with torch.no_grad():
+        logits_per_image, logits_per_text = model(image, text)
+        similarity = logits_per_image.softmax(dim=-1).cpu().numpy()
+    index = np.argmax(similarity, axis=1)
+    ref = g["logits_per_image"]
+    err = np.abs(logits_per_image.float().cpu().numpy() - ref).max()
+    assert err <= LOGIT_TOL, f"logits max abs err {err}"
+    top2 = np.sort(ref, axis=1)[:, -2:]
+    decided = (top2[:, 1] - top2[:, 0]) > 2 * LOGIT_TOL
+    assert np.array_equal(index[decided], ref.argmax(1)[decided])
+    assert torch.equal(logits_per_text, logits_per_image.t())
+
+
+def test_reference_finetune_loop_moves_weights_at_lr_1e5(tmp_path):
+    """CLIP/train.py:143-171 verbatim with lr = 1e-5 on the model clip.load returns: the weights must move
+    (bf16 parameters would round every update away) and the next forward must see them."""
+    name, B = "ViT-B/32", 8
+    orc = oracle_model(name)
+    model, _, device = _clip_load_cuda(tmp_path, orc)
+    model = model.to(device)
+    model.train()
+    try:
+        from transformers import AdamW   # the reference's optimiser, when this transformers still ships it
+        optimizer = AdamW(model.parameters(), lr=1e-5, no_deprecation_warning=True)
+    except Exception:
+        optimizer = torch.optim.AdamW(model.parameters(), lr=1e-5, eps=1e-6, weight_decay=0.0)
+    criterion = torch.nn.CrossEntropyLoss()
+    img, tok = _inputs(name, B, B, 12)
+    w0 = {n: p.detach().clone() for n, p in model.named_parameters()}
+    losses = []
+    for _ in range(4):
+        model.zero_grad()
+        image, text = img.to(device), tok.to(device)
+        logits_per_image, logits_per_text = model(image, text)
+        label = torch.arange(logits_per_image.shape[0]).to(device)
+        loss = (criterion(logits_per_image, label) + criterion(logits_per_text, label)) / 2
+        loss.backward()
+        optimizer.step()
+        optimizer.zero_grad()
+        losses.append(loss.item())
+    moved = {n: (p.detach() - w0[n]).abs().max().item() for n, p in model.named_parameters()}
+    frozen = [n for n, d in moved.items() if d == 0.0 and not n.endswith("in_proj_bias")]
+    assert not frozen, f"parameters that never moved at lr=1e-5: {frozen[:5]} (+{len(frozen) - 5})"
+    assert all(p.dtype == torch.float32 for p in model.parameters())
+    assert losses[-1] < losses[0], losses          # same batch four times: the loss must go down
+
+
+def test_trainer_keeps_state_dict_fresh():
+    """ClipTrainer updates flat master weights; model.state_dict() (CLIP/train.py:210-216 saves it) must hand back
+    the trained weights for fp32 parameters too, without an explicit write_back()."""
+    from construction_clip_b200.train import ClipTrainer
+    name, B = "tiny", 8
+    orc = oracle_model(name)
+    img, tok = _inputs(name, B, B, 12)
+    m = device_model(name, orc, dtype=torch.float32).train()
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    tr = ClipTrainer(m, lr=1e-3, warmup_steps=0)
+    for _ in range(3):
+        tr.step(img.cuda(), tok.cuda())
+    after = m.state_dict()
+    changed = [k for k in before if not torch.equal(before[k], after[k])]
+    assert len(changed) >= len(before) - 2, sorted(set(before) - set(changed))
+    # and they are the master weights, not a bf16 rounding of them
+    full = tr.master["visual"]
+    name0, p0, o0, s0 = tr.stores["visual"].entries[0]
+    assert torch.equal(after["visual." + name0].reshape(-1), full[o0:o0 + p0.numel()])
