@@ -49,7 +49,7 @@ def emit(line: dict):
     out.write(json.dumps(line) + "\n")
     out.flush()
 
-GLOBAL_BATCH = 1024
+GLOBAL_BATCH = int(os.environ.get("BENCH_GLOBAL_BATCH", "1024"))   # 1024 = BASELINE configs[1]; other values are tuning runs, not the headline
 SEED = 567
 CPU_SAMPLE_PAIRS = 32
 
@@ -144,13 +144,54 @@ def run_reference(args):
         "unit": "pairs/s", "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"CLIP {args.model} contrastive fine-tune step (CLIP/train.py:157-171), CPU oracle, "
-                               f"{CPU_SAMPLE_PAIRS}-pair bounded sample of the 1024-pair global batch"},
+                               f"{CPU_SAMPLE_PAIRS}-pair bounded sample of the 1024-pair global batch",
+                   "global_batch": CPU_SAMPLE_PAIRS, "sample_of_global_batch": GLOBAL_BATCH, "parallelism": "cpu"},
         "cpu_baseline": {"value": rate, "unit": "pairs/s", "cores": cores, "kind": "port",
                          "sample": f"{CPU_SAMPLE_PAIRS} pairs/step, fwd+loss+bwd+AdamW, fp32, median of {steps}"},
         "e2e": {"value": rate, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
+
+
+def torch_eager_bf16_rate(model_name, pairs, steps, warmup, dev):
+    """The GPU-side bar: the restated upstream module run by PyTorch eager in bf16 on the same
+    B200 -- cuBLAS GEMMs, nn.MultiheadAttention's SDPA path, ATen LayerNorm / softmax / CE, fused torch AdamW --
+    i.e. what the reference's CLIP/train.py:157-171 executes (it ships no kernel of its own), bf16 for fp16.
+    Secondary figure, taken after every headline number; none of this repository's kernels run here."""
+    import torch
+    from oracle import clip_oracle as ORC
+    cfg = ORC.CONFIGS[model_name]
+    model = ORC.build(model_name, seed=SEED).to(dev).to(torch.bfloat16).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-5, eps=1e-6, weight_decay=0.0, fused=True)
+    img = ORC.synth_images(pairs, cfg.image_resolution, seed=SEED).to(dev).to(torch.bfloat16)
+    tok = ORC.synth_tokens(pairs, seed=SEED).to(dev)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        lpi, lpt = model(img, tok)
+        loss = ORC.clip_loss(lpi, lpt)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"value": pairs / (ms * 1e-3), "unit": "pairs/s", "ms_per_step": ms, "pairs_per_step": pairs,
+           "loss": float(loss.item()), "torch": torch.__version__,
+           "what": "PyTorch eager bf16 of the restated upstream module (cuBLAS + SDPA + ATen + fused AdamW), same step, "
+                   "same B200, device-resident inputs; not this repository's kernels"}
+    del model, opt, img, tok
+    torch.cuda.empty_cache()
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -245,6 +286,11 @@ def run_ours(args):
     # on two streams (and, for small per-GPU batches, inside a CUDA-graph replay), so kernels overlap
     # and cannot be bracketed one by one; their durations are therefore taken with CUDA events around
     # every GEMM launch in serialised (single-stream, eager) steps run right after the timed region.
+    trainer_graph_ok = trainer._use_graph and len(trainer._graphs) > 0   # False: capture failed, eager fallback ran
+    graphs_captured = len(trainer._graphs)
+    from construction_clip_b200 import towers as TW
+    text_rows = [trainer.text_rows(tk) for _, tk in dev_batches]   # static rows of the packed text tower per batch
+    real_rows = [int((tk.argmax(-1) + 1).sum().item()) for _, tk in dev_batches]
     trainer.enable_cuda_graph(False)
     trainer.two_streams = False
     n0 = L.launch_count()
@@ -260,12 +306,14 @@ def run_ours(args):
     torch.cuda.synchronize()
     gemm_prof, O.GEMM_PROFILE = O.GEMM_PROFILE, None
     instr_ms = i0.elapsed_time(i1)
-    if use_graph:
+    if trainer_graph_ok:
         launches = (L.launch_count() - n0) // (n_instr + 1) * args.steps   # launches one replay contains x steps
+    graph_captured = bool(trainer_graph_ok)
     trainer.two_streams = True
     trainer.enable_cuda_graph(use_graph)
     gemm_ms = sum(a.elapsed_time(b) for a, b, _, _ in gemm_prof)
     gemm_flops = sum(f for _, _, f, _ in gemm_prof)
+    exec_flops_step = gemm_flops / n_instr   # executed GEMM FLOPs of one step on this rank
     gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     gemm_alg_bytes = sum(info[5] for _, _, _, info in gemm_prof) / max(1, len(gemm_prof))
     traffic = None
@@ -288,38 +336,6 @@ def run_ours(args):
     e2e_value = GLOBAL_BATCH * args.steps / (e2e_ms * 1e-3)
     _ = float(slot.item())
 
-    # ---------------- secondary, NOT the headline: the opt-in packed text tower ----------------
-    # (towers.PACK_TEXT: captions packed to EOT + 1 tokens -- same features / loss / gradients, see
-    # DESIGN.md §9.1.)  Single GPU only, eager launches, after every headline number has been taken; any
-    # failure here is recorded and cannot touch the figures above.
-    variants = {}
-    if world == 1 and os.environ.get("B200CLIP_BENCH_VARIANTS", "1") != "0":
-        try:
-            from construction_clip_b200 import towers as _T
-            was = _T.PACK_TEXT
-            _T.PACK_TEXT = True
-            try:
-                for i in range(2):
-                    trainer.step(*dev_batches[i % n_host])
-                torch.cuda.synchronize()
-                p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                p0.record()
-                for i in range(args.steps):
-                    ploss = trainer.step(*dev_batches[i % n_host])
-                p1.record()
-                torch.cuda.synchronize()
-                pms = p0.elapsed_time(p1) / args.steps
-                variants["packed_text"] = {
-                    "value": GLOBAL_BATCH / (pms * 1e-3), "unit": "pairs/s", "ms_per_step": pms,
-                    "loss": float(ploss.item()),
-                    "note": "opt-in B200CLIP_PACK_TEXT=1: text tower on sum(caption lengths) rows instead of B x 77 "
-                            "(positions after EOT are dead under the causal mask: identical features, loss and "
-                            "gradients); eager launches, device-resident inputs; not the headline configuration"}
-            finally:
-                _T.PACK_TEXT = was
-        except Exception as exc:  # noqa: BLE001 -- a secondary figure must never break the contract line
-            variants["packed_text"] = {"error": repr(exc)[:300]}
-
     def shutdown():
         # Drop captured graphs (they hold NCCL kernels) BEFORE the communicator goes away, and leave
         # through os._exit: tearing down NCCL with live graph state has been seen to hang at exit.
@@ -336,6 +352,22 @@ def run_ours(args):
     if rank != 0:
         shutdown()
         return
+
+    # secondary: the library bar on the same GPU (N = 1 only; after every number of ours has been taken)
+    variants = {}
+    if world == 1 and os.environ.get("B200CLIP_BENCH_VARIANTS", "1") != "0":
+        try:
+            trainer.enable_cuda_graph(False)
+            trainer.grads = trainer.master = trainer.m = trainer.v = None   # hand the memory back first
+            del dev_batches
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            variants["torch_eager_bf16"] = torch_eager_bf16_rate(args.model, GLOBAL_BATCH, steps=min(args.steps, 5),
+                                                                 warmup=3, dev=dev)
+            variants["torch_eager_bf16"]["ours_over_torch_eager"] = value / variants["torch_eager_bf16"]["value"]
+        except Exception as exc:  # noqa: BLE001 -- a secondary figure must never break the contract line
+            variants["torch_eager_bf16"] = {"error": repr(exc)[:300]}
 
     peaks = load_peaks()
     f_pair = 3.0 * ORC.flops_pair(ORC.CONFIGS[args.model])          # algorithmic FLOPs per trained pair
@@ -355,13 +387,28 @@ def run_ours(args):
             "workload": f"CLIP {args.model} contrastive fine-tune step (CLIP/train.py:157-171): fwd both towers, "
                         f"all-gathered symmetric InfoNCE, bwd, grad all-reduce, AdamW; global batch {GLOBAL_BATCH} "
                         f"({bl}/GPU), 224x224 images, 77-token prompts, random-init weights seed {SEED}",
-            "global_batch": GLOBAL_BATCH, "per_gpu_batch": bl, "parallelism": f"dp{world}", "cuda_graph": use_graph,
+            "global_batch": GLOBAL_BATCH, "per_gpu_batch": bl, "parallelism": f"dp{world}",
+            "cuda_graph": graph_captured, "cuda_graphs_captured": graphs_captured,
+            "packed_text": {
+                "on": bool(TW.PACK_TEXT and text_rows[0] is not None),
+                "why": "under upstream's causal mask nothing after a caption's EOT reaches the pooled feature, and those "
+                       "positions get exactly-zero gradients: the text tower runs on sum(EOT position + 1) rows (rounded "
+                       "up to a bucket) instead of per_gpu_batch x 77; same features / loss / gradients "
+                       "(tests/test_model_gpu.py::test_packed_text_train_step_vs_oracle_b64)",
+                "caption_lengths": "U{3..76} tokens + EOT (SURVEY 8(d) synthetic recipe)",
+                "rows_executed_per_batch": text_rows, "rows_real_per_batch": real_rows, "rows_unpacked": bl * 77},
             "l2_policy": "inputs and per-step activations (>10 GB/step) exceed the 126 MB L2; no explicit flush",
             "final_loss": final_loss,
             "algorithmic_gflop_per_pair": f_pair / 1e9,
             "step_tflops_per_gpu": step_tflops_per_gpu,
             "step_frac_of_bf16_sustained_peak": step_tflops_per_gpu / peaks["bf16_sustained"],
             "step_frac_of_bf16_burst_peak": step_tflops_per_gpu / peaks["bf16_burst"],
+            # the same step counted by the GEMM FLOPs the kernels actually EXECUTED (packed text tower, pooled last
+            # block): sum of 2MNK over every GEMM launch of one step, attention excluded (< 1 %)
+            "executed_gemm_gflop_per_pair": exec_flops_step / bl / 1e9,
+            "executed_over_algorithmic_flops": exec_flops_step / bl / f_pair,
+            "step_executed_tflops_per_gpu": value / world * (exec_flops_step / bl) / 1e12,
+            "step_executed_frac_of_bf16_burst_peak": value / world * (exec_flops_step / bl) / 1e12 / peaks["bf16_burst"],
         },
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
                 "ms_per_step": e2e_ms / args.steps},
@@ -378,7 +425,7 @@ def run_ours(args):
             "launches_timed": len(gemm_prof),
             "how": "CUDA events around every GEMM launch in 2 serialised eager steps right after the timed region "
                    "(the timed region overlaps the two towers on two streams"
-                   + (" inside a CUDA-graph replay)" if use_graph else ")"),
+                   + (" inside a CUDA-graph replay)" if graph_captured else ")"),
             "share_of_step": gemm_ms / instr_ms,
             "algorithmic_flops_per_launch_avg": gemm_flops / max(1, len(gemm_prof)),
         },

@@ -34,7 +34,24 @@ struct AttnParams {
     // packed ("varlen") rows: sample b owns rows cu[b] .. cu[b+1]-1 (at most S of them) of qkv / out /
     // dqkv, and lse is indexed [row * H + h].  nullptr: every sample owns S rows, lse [(b*H + h)*S + r].
     const int32_t* cu;
+    // packed rows with a STATIC row count (CUDA-graph buckets): rows cu[B] .. total_rows-1 belong to no sample.
+    // The kernels zero-fill them in their output (out_ld elements per row) so that everything downstream
+    // (row-wise GEMMs / LayerNorms, and the token-reductions of the weight gradients) sees finite zeros.
+    int total_rows, out_ld;
 };
+
+// zero-fill of the surplus rows of a packed output (see AttnParams::total_rows); the whole grid takes part
+template <bool VARLEN>
+__device__ __forceinline__ void zero_surplus_rows(const AttnParams& p) {
+    if constexpr (VARLEN) {
+        const int live = min(__ldg(p.cu + p.B), p.total_rows);
+        const int64_t n16 = static_cast<int64_t>(p.total_rows - live) * p.out_ld / 8;   // uint4 = 8 bf16
+        uint4* base = reinterpret_cast<uint4*>(p.out + static_cast<int64_t>(live) * p.out_ld);
+        for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n16;
+             i += static_cast<int64_t>(gridDim.x) * blockDim.x)
+            base[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
 
 // rows and length of work item b
 template <bool VARLEN>
@@ -151,6 +168,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
     griddep_launch_dependents();
     griddep_wait();  // the prologue above overlapped the previous kernel's tail; global memory from here on
     if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < num_work) issue_loads(blockIdx.x);
+    zero_surplus_rows<VARLEN>(p);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
         const int b = w / H, h = w - b * H;
@@ -500,6 +518,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     griddep_launch_dependents();
     griddep_wait();  // the prologue above overlapped the previous kernel's tail; global memory from here on
     if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < num_work) issue_loads(blockIdx.x);
+    zero_surplus_rows<VARLEN>(p);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
         const int b = w / H, h = w - b * H;
@@ -1055,6 +1074,8 @@ extern "C" int b200clip_attn_fwd_varlen(b200clip_ctx* ctx, const void* qkv, void
     p.causal = causal ? 1 : 0;
     p.npad = static_cast<int>((S_max + 15) / 16 * 16);
     p.cu = cu;
+    p.total_rows = static_cast<int>(total_rows);
+    p.out_ld = static_cast<int>(H * 64);
     const bool big = S_max > 64;
     const int smem = fwd_smem(big, p.npad);
     const int per_sm = ctas_per_sm(smem, big ? 128 : 64, 8);
@@ -1093,6 +1114,8 @@ extern "C" int b200clip_attn_bwd_varlen(b200clip_ctx* ctx, const void* qkv, cons
     p.causal = causal ? 1 : 0;
     p.npad = static_cast<int>((S_max + 15) / 16 * 16);
     p.cu = cu;
+    p.total_rows = static_cast<int>(total_rows);
+    p.out_ld = static_cast<int>(3 * H * 64);
     const bool big = S_max > 64;
     const int smem = bwd_smem(big, p.npad);
     const int per_sm = ctas_per_sm(smem, 256, 2);

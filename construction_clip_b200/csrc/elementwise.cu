@@ -43,6 +43,123 @@ embed_tokens_fwd_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Packed text tower.  Under upstream's causal mask (clip.model.CLIP.build_attention_mask) nothing after a
+// caption's EOT token can reach the pooled feature x[arange, text.argmax(-1)], and those positions
+// receive exactly-zero gradients -- so they need not exist: caption b keeps len_b = argmax_s ids[b,s] + 1
+// rows, the captions are stored back to back (cu = exclusive prefix sum of len), and every row-wise
+// kernel simply sees fewer rows.  One block: a warp per caption finds its length, then a block-wide scan.
+__global__ void __launch_bounds__(1024)
+text_pack_plan_kernel(const int32_t* __restrict__ ids, int32_t* __restrict__ cu, int32_t* __restrict__ eot_row,
+                      int B, int S, int rows_cap) {
+    __shared__ int s_len[1024];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        s_carry = 0;
+        cu[0] = 0;
+    }
+    for (int base = 0; base < B; base += 1024) {
+        const int nb = min(1024, B - base);
+        __syncthreads();
+        for (int i = warp; i < nb; i += 32) {  // first arg-max of ids[base + i, :]
+            int best = INT32_MIN, best_s = S;
+            for (int t = lane; t < S; t += 32) {
+                const int v = ids[static_cast<int64_t>(base + i) * S + t];
+                if (v > best) {
+                    best = v;
+                    best_s = t;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const int ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int os = __shfl_xor_sync(0xffffffffu, best_s, o);
+                if (ov > best || (ov == best && os < best_s)) {
+                    best = ov;
+                    best_s = os;
+                }
+            }
+            if (lane == 0) s_len[i] = best_s + 1;
+        }
+        __syncthreads();
+        // inclusive scan of s_len[0 .. nb) (Hillis-Steele; one element per thread)
+        int v = threadIdx.x < nb ? s_len[threadIdx.x] : 0;
+        for (int o = 1; o < 1024; o <<= 1) {
+            __syncthreads();
+            const int add = (static_cast<int>(threadIdx.x) >= o) ? s_len[threadIdx.x - o] : 0;
+            __syncthreads();
+            if (threadIdx.x < nb) {
+                v += add;
+                s_len[threadIdx.x] = v;
+            }
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        if (threadIdx.x < nb) {
+            // never hand out rows past the caller's buffer: a too-small `rows_cap` truncates captions
+            // (wrong features) instead of corrupting memory
+            const int end = min(carry + v, rows_cap);
+            cu[base + threadIdx.x + 1] = end;
+            eot_row[base + threadIdx.x] = max(end - 1, 0);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = carry + s_len[nb - 1];
+    }
+}
+
+// token_embedding(text) + positional_embedding written straight into the packed layout; rows cu[B] .. rows_total-1
+// (static-shape surplus) are zero-filled.
+template <typename TOut>
+__global__ void __launch_bounds__(256)
+embed_tokens_packed_fwd_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __restrict__ table,
+                               const __nv_bfloat16* __restrict__ pos, const int32_t* __restrict__ cu,
+                               TOut* __restrict__ out, int B, int S, int d, int vocab, int rows_total) {
+    const int lane = threadIdx.x & 31;
+    const int nvec = d >> 3;
+    const int live = min(__ldg(cu + B), rows_total);
+    const int total = B * S + (rows_total - live);   // (b, s) slots, then the surplus rows
+    for (int t = blockIdx.x * 8 + (threadIdx.x >> 5); t < total; t += gridDim.x * 8) {
+        if (t >= B * S) {   // zero a surplus row
+            TOut* dst = out + static_cast<int64_t>(live + (t - B * S)) * d;
+            for (int vec = lane; vec < nvec; vec += 32) {
+                if constexpr (sizeof(TOut) == 2) {
+                    *reinterpret_cast<uint4*>(dst + vec * 8) = make_uint4(0u, 0u, 0u, 0u);
+                } else {
+                    *reinterpret_cast<float4*>(dst + vec * 8) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    *reinterpret_cast<float4*>(dst + vec * 8 + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            continue;
+        }
+        const int b = t / S, sp = t - b * S;
+        const int row0 = __ldg(cu + b);
+        if (sp >= __ldg(cu + b + 1) - row0) continue;   // after the EOT token: the position does not exist
+        int id = ids[t];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        for (int vec = lane; vec < nvec; vec += 32) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(table + static_cast<int64_t>(id) * d + vec * 8));
+            const uint4 bq = __ldg(reinterpret_cast<const uint4*>(pos + static_cast<int64_t>(sp) * d + vec * 8));
+            const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {bq.x, bq.y, bq.z, bq.w};
+            float o[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 fa = unpack_bf16(aw[j]), fb = unpack_bf16(bw[j]);
+                o[2 * j] = fa.x + fb.x;
+                o[2 * j + 1] = fa.y + fb.y;
+            }
+            TOut* dst = out + static_cast<int64_t>(row0 + sp) * d + vec * 8;
+            if constexpr (sizeof(TOut) == 2) {
+                *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(o[0], o[1]), pack_bf16(o[2], o[3]),
+                                                            pack_bf16(o[4], o[5]), pack_bf16(o[6], o[7]));
+            } else {
+                *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+            }
+        }
+    }
+}
+
 // eot_row[b] = b*S + argmax_s ids[b,s]  (first maximum, like torch.argmax)
 __global__ void eot_argmax_kernel(const int32_t* __restrict__ ids, int32_t* __restrict__ eot_row, int B, int S) {
     const int lane = threadIdx.x & 31;
@@ -73,7 +190,8 @@ __global__ void eot_argmax_kernel(const int32_t* __restrict__ ids, int32_t* __re
 // the causal mask) and keeps the positional gradient in registers until the end.
 __global__ void __launch_bounds__(256)
 embed_tokens_bwd_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __restrict__ dout,
-                        float* __restrict__ dtable, float* __restrict__ dpos, int B, int S, int d, int vocab) {
+                        float* __restrict__ dtable, float* __restrict__ dpos, int B, int S, int d, int vocab,
+                        const int32_t* __restrict__ cu) {  // cu != nullptr: dout is in the packed layout
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int s = blockIdx.x;
@@ -86,7 +204,12 @@ embed_tokens_bwd_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = 0.f;
         for (int b = wid; b < B; b += warps_total) {
-            const int64_t r = static_cast<int64_t>(b) * S + s;
+            int64_t r = static_cast<int64_t>(b) * S + s;
+            if (cu != nullptr) {
+                const int row0 = __ldg(cu + b);
+                if (s >= __ldg(cu + b + 1) - row0) continue;   // position dropped by the packing: zero gradient
+                r = row0 + s;
+            }
             float f[8];
             bool nz = false;
             if (vec < nvec) {
@@ -101,7 +224,7 @@ embed_tokens_bwd_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __
                 }
             }
             if (nz) {
-                int id = ids[r];
+                int id = ids[static_cast<int64_t>(b) * S + s];
                 id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
                 float* dst = dtable + static_cast<int64_t>(id) * d + vec * 8;
 #pragma unroll
@@ -117,6 +240,21 @@ embed_tokens_bwd_kernel(const int32_t* __restrict__ ids, const __nv_bfloat16* __
             for (int j = 0; j < 8; ++j)
                 if (acc[j] != 0.f) atomicAdd(dst + j, acc[j]);
         }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row gather / scatter for the pooled last block (towers.py: only the CLS / EOT token of the last block's
+// out_proj / ln_2 / MLP is live): dst[i,:] = src[idx[i],:]  /  dst[idx[i],:] = src[i,:], 16-byte vectors.
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(const uint4* __restrict__ src, int64_t src_ld16, const int32_t* __restrict__ idx,
+                   uint4* __restrict__ dst, int n, int row16, bool scatter) {
+    const int lane = threadIdx.x & 31;
+    for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += gridDim.x * 8) {
+        const int64_t r = idx[i];
+        const uint4* sp = scatter ? src + static_cast<int64_t>(i) * row16 : src + r * src_ld16;
+        uint4* dp = scatter ? dst + r * src_ld16 : dst + static_cast<int64_t>(i) * row16;
+        for (int v = lane; v < row16; v += 32) dp[v] = sp[v];
     }
 }
 
@@ -387,7 +525,94 @@ extern "C" int b200clip_embed_tokens_bwd(b200clip_ctx* ctx, const int32_t* ids, 
     dim3 grid(static_cast<unsigned>(S), static_cast<unsigned>(chunks));
     embed_tokens_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         ids, static_cast<const __nv_bfloat16*>(dout), dtable, dpos, static_cast<int>(B), static_cast<int>(S),
-        static_cast<int>(d), static_cast<int>(vocab));
+        static_cast<int>(d), static_cast<int>(vocab), nullptr);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200clip_gather_rows(b200clip_ctx* ctx, const void* src, int64_t src_ld_bytes, const int32_t* idx,
+                                    void* dst, int64_t n, int64_t row_bytes, void* stream) {
+    B200_CHECK_CTX(ctx);
+    B200_CHECK_ARG(src && idx && dst && n > 0 && n < (1ll << 31), "gather_rows: bad argument");
+    B200_CHECK_ARG(row_bytes > 0 && row_bytes % 16 == 0 && src_ld_bytes % 16 == 0 && src_ld_bytes >= row_bytes &&
+                       (reinterpret_cast<uintptr_t>(src) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                   "gather_rows: rows must be 16-byte multiples, 16-byte aligned");
+    gather_rows_kernel<<<grid_for(ceil_div(n, 8) * 256, 256, ctx->num_sms), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(src), src_ld_bytes / 16, idx, static_cast<uint4*>(dst), static_cast<int>(n),
+        static_cast<int>(row_bytes / 16), false);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200clip_scatter_rows(b200clip_ctx* ctx, const void* src, const int32_t* idx, void* dst,
+                                     int64_t dst_rows, int64_t n, int64_t row_bytes, int zero_first, void* stream) {
+    B200_CHECK_CTX(ctx);
+    B200_CHECK_ARG(src && idx && dst && n > 0 && n < (1ll << 31) && dst_rows > 0, "scatter_rows: bad argument");
+    B200_CHECK_ARG(row_bytes > 0 && row_bytes % 16 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(dst) & 15) == 0,
+                   "scatter_rows: rows must be 16-byte multiples, 16-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (zero_first) B200_CHECK_CUDA(cudaMemsetAsync(dst, 0, static_cast<size_t>(dst_rows * row_bytes), st));
+    gather_rows_kernel<<<grid_for(ceil_div(n, 8) * 256, 256, ctx->num_sms), 256, 0, st>>>(
+        static_cast<const uint4*>(src), row_bytes / 16, idx, static_cast<uint4*>(dst), static_cast<int>(n),
+        static_cast<int>(row_bytes / 16), true);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200clip_text_pack_plan(b200clip_ctx* ctx, const int32_t* ids, int32_t* cu, int32_t* eot_row, int64_t B,
+                                       int64_t S, int64_t rows_cap, void* stream) {
+    B200_CHECK_CTX(ctx);
+    B200_CHECK_ARG(ids && cu && eot_row, "text_pack_plan: null pointer");
+    B200_CHECK_ARG(B > 0 && S > 0 && B * S < (1ll << 31) && rows_cap > 0 && rows_cap < (1ll << 31),
+                   "text_pack_plan: bad shape");
+    text_pack_plan_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(ids, cu, eot_row, static_cast<int>(B),
+                                                                            static_cast<int>(S),
+                                                                            static_cast<int>(rows_cap));
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200clip_embed_tokens_packed_fwd(b200clip_ctx* ctx, const int32_t* ids, const void* table,
+                                                const void* pos, const int32_t* cu, void* out, int out_dtype, int64_t B,
+                                                int64_t S, int64_t d, int64_t vocab, int64_t rows_total, void* stream) {
+    B200_CHECK_CTX(ctx);
+    B200_CHECK_ARG(ids && table && pos && cu && out, "embed_tokens_packed_fwd: null pointer");
+    B200_CHECK_ARG(B > 0 && S > 0 && d > 0 && d % 8 == 0 && vocab > 0 && B * S < (1ll << 30) && rows_total > 0 &&
+                       rows_total < (1ll << 30),
+                   "embed_tokens_packed_fwd: bad shape");
+    B200_CHECK_ARG(out_dtype == B200CLIP_DT_BF16 || out_dtype == B200CLIP_DT_F32, "embed_tokens_packed_fwd: bad out_dtype");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int grid = grid_for(ceil_div(B * S + rows_total, 8) * 256, 256, ctx->num_sms);
+    if (out_dtype == B200CLIP_DT_BF16)
+        embed_tokens_packed_fwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(
+            ids, static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(pos), cu,
+            static_cast<__nv_bfloat16*>(out), static_cast<int>(B), static_cast<int>(S), static_cast<int>(d),
+            static_cast<int>(vocab), static_cast<int>(rows_total));
+    else
+        embed_tokens_packed_fwd_kernel<float><<<grid, 256, 0, st>>>(
+            ids, static_cast<const __nv_bfloat16*>(table), static_cast<const __nv_bfloat16*>(pos), cu,
+            static_cast<float*>(out), static_cast<int>(B), static_cast<int>(S), static_cast<int>(d),
+            static_cast<int>(vocab), static_cast<int>(rows_total));
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200clip_embed_tokens_packed_bwd(b200clip_ctx* ctx, const int32_t* ids, const void* dout,
+                                                const int32_t* cu, float* dtable, float* dpos, int64_t B, int64_t S,
+                                                int64_t d, int64_t vocab, void* stream) {
+    B200_CHECK_CTX(ctx);
+    B200_CHECK_ARG(ids && dout && cu && dtable && dpos, "embed_tokens_packed_bwd: null pointer");
+    B200_CHECK_ARG(B > 0 && S > 0 && d > 0 && d % 8 == 0 && vocab > 0 && B * S < (1ll << 31),
+                   "embed_tokens_packed_bwd: bad shape");
+    int chunks = static_cast<int>(ceil_div(static_cast<int64_t>(ctx->num_sms) * 4, S));
+    const int max_chunks = static_cast<int>(ceil_div(B, 8));
+    if (chunks > max_chunks) chunks = max_chunks;
+    if (chunks < 1) chunks = 1;
+    dim3 grid(static_cast<unsigned>(S), static_cast<unsigned>(chunks));
+    embed_tokens_bwd_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        ids, static_cast<const __nv_bfloat16*>(dout), dtable, dpos, static_cast<int>(B), static_cast<int>(S),
+        static_cast<int>(d), static_cast<int>(vocab), cu);
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -38,6 +38,11 @@ SIGNATURES = {
     "b200clip_attn_bwd_varlen": [_p, _p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _i, _p],
     "b200clip_embed_tokens_fwd": [_p, _p, _p, _p, _p, _i, _p, _l, _l, _l, _l, _p],
     "b200clip_embed_tokens_bwd": [_p, _p, _p, _p, _p, _l, _l, _l, _l, _p],
+    "b200clip_text_pack_plan": [_p, _p, _p, _p, _l, _l, _l, _p],
+    "b200clip_embed_tokens_packed_fwd": [_p, _p, _p, _p, _p, _p, _i, _l, _l, _l, _l, _l, _p],
+    "b200clip_embed_tokens_packed_bwd": [_p, _p, _p, _p, _p, _p, _l, _l, _l, _l, _p],
+    "b200clip_gather_rows": [_p, _p, _l, _p, _p, _l, _l, _p],
+    "b200clip_scatter_rows": [_p, _p, _p, _p, _l, _l, _l, _i, _p],
     "b200clip_im2col_patch": [_p, _p, _i, _p, _l, _l, _l, _l, _p],
     "b200clip_colsum": [_p, _p, _l, _p, _l, _l, _p],
     "b200clip_vision_assemble_bwd": [_p, _p, _p, _p, _p, _l, _l, _l, _p],

@@ -136,14 +136,14 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dgamma, dbeta, *, row_index=None, dr
 
 
 # ------------------------------------------------------------------------------------- attention
-def attn_fwd(qkv, B, S, H, causal, out=None, want_lse=False, cu=None, zero_fill=False):
-    """``cu`` (int32 [B+1]): packed rows -- sample b owns rows cu[b] .. cu[b+1]-1 (<= S) of ``qkv``;
-    ``zero_fill``: rows past cu[B] exist (static-shape packing) and must read as zeros."""
+def attn_fwd(qkv, B, S, H, causal, out=None, want_lse=False, cu=None):
+    """``cu`` (int32 [B+1]): packed rows -- sample b owns rows cu[b] .. cu[b+1]-1 (<= S) of ``qkv``; rows
+    past cu[B] (the surplus of a static row count) are zero-filled in ``out`` by the kernel."""
     if cu is not None:
         rows = qkv.shape[0]
         assert qkv.dtype == bf16 and qkv.is_contiguous() and qkv.shape[1] == 3 * H * 64 and cu.dtype == i32
         if out is None:
-            out = (torch.zeros if zero_fill else torch.empty)((rows, H * 64), device=qkv.device, dtype=bf16)
+            out = torch.empty((rows, H * 64), device=qkv.device, dtype=bf16)
         lse = torch.empty(rows * H, device=qkv.device, dtype=f32) if want_lse else None
         ctx, st = _ctx_stream(qkv)
         L.check(L.load().b200clip_attn_fwd_varlen(ctx, qkv.data_ptr(), out.data_ptr(), _ptr(lse), cu.data_ptr(), B, S, H,
@@ -159,12 +159,12 @@ def attn_fwd(qkv, B, S, H, causal, out=None, want_lse=False, cu=None, zero_fill=
     return (out, lse) if want_lse else out
 
 
-def attn_bwd(qkv, out, lse, dout, B, S, H, causal, dqkv=None, cu=None, zero_fill=False):
+def attn_bwd(qkv, out, lse, dout, B, S, H, causal, dqkv=None, cu=None):
     if cu is not None:
         rows = qkv.shape[0]
         assert qkv.is_contiguous() and dout.is_contiguous() and out.is_contiguous() and dout.shape == (rows, H * 64)
         if dqkv is None:
-            dqkv = torch.zeros_like(qkv) if zero_fill else torch.empty_like(qkv)
+            dqkv = torch.empty_like(qkv)
         ctx, st = _ctx_stream(qkv)
         L.check(L.load().b200clip_attn_bwd_varlen(ctx, qkv.data_ptr(), out.data_ptr(), lse.data_ptr(), dout.data_ptr(),
                                                   dqkv.data_ptr(), cu.data_ptr(), B, S, H, rows, 1 if causal else 0, st),
@@ -201,6 +201,64 @@ def embed_tokens_bwd(ids, dout, dtable, dpos):
     ctx, st = _ctx_stream(dout)
     L.check(L.load().b200clip_embed_tokens_bwd(ctx, ids.data_ptr(), dout.data_ptr(), dtable.data_ptr(), dpos.data_ptr(),
                                                B, S, d, V, st), "embed_tokens_bwd")
+
+
+def text_pack_plan(ids, rows_cap):
+    """-> (cu int32 [B+1], eot_row int32 [B]) of the packed text layout (caption b keeps argmax + 1 rows)."""
+    B, S = ids.shape
+    assert ids.dtype == i32 and ids.is_contiguous()
+    cu = torch.empty(B + 1, device=ids.device, dtype=i32)
+    eot = torch.empty(B, device=ids.device, dtype=i32)
+    ctx, st = _ctx_stream(ids)
+    L.check(L.load().b200clip_text_pack_plan(ctx, ids.data_ptr(), cu.data_ptr(), eot.data_ptr(), B, S, int(rows_cap), st),
+            "text_pack_plan")
+    return cu, eot
+
+
+def embed_tokens_packed_fwd(ids, table, pos, cu, rows_total, out_dtype=bf16):
+    B, S = ids.shape
+    V, d = table.shape
+    assert ids.dtype == i32 and ids.is_contiguous() and table.is_contiguous() and pos.is_contiguous() and cu.dtype == i32
+    out = torch.empty((int(rows_total), d), device=table.device, dtype=out_dtype)
+    ctx, st = _ctx_stream(table)
+    L.check(L.load().b200clip_embed_tokens_packed_fwd(ctx, ids.data_ptr(), table.data_ptr(), pos.data_ptr(), cu.data_ptr(),
+                                                      out.data_ptr(), _dt(out), B, S, d, V, int(rows_total), st),
+            "embed_tokens_packed_fwd")
+    return out
+
+
+def embed_tokens_packed_bwd(ids, dout, cu, dtable, dpos):
+    B, S = ids.shape
+    V, d = dtable.shape
+    assert dout.is_contiguous() and dout.dtype == bf16 and dtable.dtype == f32 and dpos.dtype == f32
+    ctx, st = _ctx_stream(dout)
+    L.check(L.load().b200clip_embed_tokens_packed_bwd(ctx, ids.data_ptr(), dout.data_ptr(), cu.data_ptr(),
+                                                      dtable.data_ptr(), dpos.data_ptr(), B, S, d, V, st),
+            "embed_tokens_packed_bwd")
+
+
+def gather_rows(src, idx):
+    """dst[i, :] = src[idx[i], :]  (idx int32)."""
+    ld = _row_major(src, "src")
+    assert idx.dtype == i32 and idx.is_contiguous()
+    n, d = idx.numel(), src.shape[1]
+    dst = torch.empty((n, d), device=src.device, dtype=src.dtype)
+    ctx, st = _ctx_stream(src)
+    es = src.element_size()
+    L.check(L.load().b200clip_gather_rows(ctx, src.data_ptr(), ld * es, idx.data_ptr(), dst.data_ptr(), n, d * es, st),
+            "gather_rows")
+    return dst
+
+
+def scatter_rows(src, idx, rows):
+    """zeros([rows, d]) with dst[idx[i], :] = src[i, :]."""
+    assert idx.dtype == i32 and idx.is_contiguous() and src.is_contiguous()
+    n, d = src.shape
+    dst = torch.empty((int(rows), d), device=src.device, dtype=src.dtype)
+    ctx, st = _ctx_stream(src)
+    L.check(L.load().b200clip_scatter_rows(ctx, src.data_ptr(), idx.data_ptr(), dst.data_ptr(), int(rows), n,
+                                           d * src.element_size(), 1, st), "scatter_rows")
+    return dst
 
 
 # ---------------------------------------------------------------------------------- patch embed

@@ -28,20 +28,19 @@ bf16, f32, i32 = torch.bfloat16, torch.float32, torch.int32
 # exists for A/B timing and for the test that proves both settings give the same features and gradients.
 POOL_LAST_BLOCK = os.environ.get("B200CLIP_POOL_LAST_BLOCK", "1") != "0"
 
-# OPT-IN (B200CLIP_PACK_TEXT=1): pack every caption to its EOT + 1 tokens.  Under upstream's causal mask
-# nothing after the EOT token can reach the pooled feature and those positions receive exactly-zero
-# gradients, so the text tower can run on sum(lengths) rows instead of B x 77 (the same dead-code
-# argument as POOL_LAST_BLOCK, applied to every block): same features, loss and gradients
-# (tests/test_model_gpu.py::test_packed_text_is_exact), 47.6 vs 59.2 ms per 1024-pair step on one B200
-# with the bench's U{3..76} caption lengths.  Off by default: it needs a host sync per call (dynamic row
-# count), so the step is not captured into a CUDA graph, and it has only been validated on one GPU.
-PACK_TEXT = os.environ.get("B200CLIP_PACK_TEXT", "0") in ("1", "2")
-# B200CLIP_PACK_TEXT=2 (NOT yet run on hardware): the same packing with STATIC shapes, so that the step can
-# be captured into CUDA graphs keyed by a row-count bucket.  The trainer sets PACK_ROWS_STATIC to the
-# bucket (>= the real row count) around its forward; the packed tensors then have exactly that many
-# rows, the surplus rows are all-zero (and stay finite / contribute nothing through every kernel).
-PACK_STATIC = os.environ.get("B200CLIP_PACK_TEXT", "0") == "2"
-PACK_ROWS_STATIC = None
+# Packed text tower (default; B200CLIP_PACK_TEXT=0 disables it).  Under upstream's causal mask nothing after a
+# caption's EOT token can reach the pooled feature x[arange, text.argmax(-1)], and those positions receive
+# exactly-zero gradients (tests/test_cpu.py::test_positions_after_eot_are_dead_in_the_oracle), so the text
+# tower runs on sum(EOT position + 1) rows instead of B x 77 -- the same dead-code argument as POOL_LAST_BLOCK,
+# applied to every block.  Same features, loss and gradients (tests/test_model_gpu.py::test_packed_text_*).
+# Shapes stay STATIC: the caller passes the row count of the packed buffers (`rows`, >= the real count --
+# ClipTrainer rounds it up to a bucket so that one CUDA graph per bucket can be replayed); the surplus rows
+# hold zeros (b200clip_embed_tokens_packed_fwd / the packed attention kernels write them), stay finite through
+# every row-wise kernel and keep exactly-zero gradients.  Without a caller-supplied count (drop-in
+# `model(image, text)`), text_fwd reads it back from the device (one host sync) and only when the batch is
+# large enough for that to pay (PACK_MIN_ROWS).
+PACK_TEXT = os.environ.get("B200CLIP_PACK_TEXT", "1") != "0"
+PACK_MIN_ROWS = int(os.environ.get("B200CLIP_PACK_MIN_ROWS", "4096"))
 
 
 @dataclass
@@ -67,7 +66,6 @@ class BlockSaved:
 class TowerSaved:
     blocks: list = field(default_factory=list)
     extra: dict = field(default_factory=dict)
-    pad: bool = False  # static-shape packing: rows past cu[B] exist and must stay zero in the gradient stream
 
 
 def _blk(prefix: str, i: int) -> str:
@@ -94,12 +92,10 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None, 
         else:
             h1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"])
         qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
-        pad = cu is not None and PACK_ROWS_STATIC is not None  # surplus rows exist: the kernels never write them
         if save:
-            saved.pad = pad
-            a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True, cu=cu, zero_fill=pad)
+            a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True, cu=cu)
         else:
-            a, lse = O.attn_fwd(qkv, B, S, H, causal, cu=cu, zero_fill=pad), None
+            a, lse = O.attn_fwd(qkv, B, S, H, causal, cu=cu), None
         x2 = O.linear_fwd(a, W[p + "attn.out_proj.weight"], W[p + "attn.out_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x,
                           out_dtype=f32)
         if save:
@@ -120,7 +116,6 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None, 
 def _last_block_fwd(W, p, x, B, S, H, causal, saved, pool_rows, cu=None):
     save = saved is not None
     if save:
-        saved.pad = cu is not None and PACK_ROWS_STATIC is not None
         h1, mean1, rstd1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"], want_stats=True)
         qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
         a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True, cu=cu)   # only pooled rows of `a` are read below
@@ -128,9 +123,9 @@ def _last_block_fwd(W, p, x, B, S, H, causal, saved, pool_rows, cu=None):
         h1, mean1, rstd1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"]), None, None
         qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
         a, lse = O.attn_fwd(qkv, B, S, H, causal, cu=cu), None
-    rows = pool_rows.long()
-    a_p = a.index_select(0, rows)   # [B, d] bf16
-    x_p = x.index_select(0, rows)   # [B, d] fp32 residual stream at the pooled tokens
+    rows = pool_rows
+    a_p = O.gather_rows(a, rows)   # [B, d] bf16
+    x_p = O.gather_rows(x, rows)   # [B, d] fp32 residual stream at the pooled tokens
     x2 = O.linear_fwd(a_p, W[p + "attn.out_proj.weight"], W[p + "attn.out_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x_p,
                       out_dtype=f32)
     if save:
@@ -176,9 +171,9 @@ def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved, on_
         d_model = gb.numel() // 3
         da = O.linear_dgrad(dx2, W[p + "attn.out_proj.weight"], colsum=gb[2 * d_model:])
         if s.pool is not None:  # pooled last block: the gradients of every other token are exactly zero
-            da = torch.zeros((s.a.shape[0], d_model), device=da.device, dtype=bf16).index_copy_(0, s.pool, da)
-            dx2 = torch.zeros((s.a.shape[0], d_model), device=da.device, dtype=bf16).index_copy_(0, s.pool, dx2)
-        dqkv = O.attn_bwd(s.qkv, s.a, s.lse, da, B, S, H, causal, cu=cu, zero_fill=saved.pad)
+            da = O.scatter_rows(da, s.pool, s.a.shape[0])
+            dx2 = O.scatter_rows(dx2, s.pool, s.a.shape[0])
+        dqkv = O.attn_bwd(s.qkv, s.a, s.lse, da, B, S, H, causal, cu=cu)
         O.colsum(dqkv[:, :d_model], gb[:d_model])
         O.linear_wgrad(dqkv, s.h1, G[p + "attn.in_proj_weight"])
         dh1 = O.linear_dgrad(dqkv, W[p + "attn.in_proj_weight"])
@@ -218,6 +213,25 @@ def _pool_project_bwd(W, G, dfeat, x, row_index, ln_w, ln_b, proj, pooled, mean,
 
 
 # ------------------------------------------------------------------------------------------------
+_VISION_INDEX = {}
+
+
+def _vision_index(B, n, device):
+    """(ridx, cls_rows): source row of every token of the assembled sequence (-1 = class embedding, else the
+    patch row) and the rows of the CLS tokens.  Depends on (B, n) only: built once per shape."""
+    key = (B, n, device)
+    hit = _VISION_INDEX.get(key)
+    if hit is None:
+        g2 = n - 1
+        ridx = torch.arange(-1, g2, device=device, dtype=i32).repeat(B, 1)
+        ridx[:, 1:] += (torch.arange(B, device=device, dtype=i32) * g2)[:, None]
+        cls_rows = torch.arange(B, device=device, dtype=i32) * n
+        if len(_VISION_INDEX) >= 16:
+            _VISION_INDEX.clear()
+        hit = _VISION_INDEX[key] = (ridx.reshape(-1).contiguous(), cls_rows)
+    return hit
+
+
 # clip.model.VisionTransformer.forward
 def vision_fwd(W, cfg, image, save: bool):
     B = image.shape[0]
@@ -229,17 +243,13 @@ def vision_fwd(W, cfg, image, save: bool):
     kpad = W["conv1.weight"].shape[1]
     cols = O.im2col_patch(image, p, ldcols=kpad)                      # [B*g*g, kpad]
     patch = O.gemm(cols, W["conv1.weight"])                           # conv1 as GEMM -> [B*g*g, d]
-    g2 = n - 1
-    ridx = torch.arange(-1, g2, device=image.device, dtype=i32).repeat(B, 1)
-    ridx[:, 1:] += (torch.arange(B, device=image.device, dtype=i32) * g2)[:, None]
-    ridx = ridx.reshape(-1)
+    ridx, cls_rows = _vision_index(B, n, image.device)
     pre = torch.empty((B * n, d), device=image.device, dtype=bf16) if save else None
     r = O.layernorm_fwd(patch, W["ln_pre.weight"], W["ln_pre.bias"], rows=B * n, row_index=ridx,
                         neg_row=W["class_embedding"], add=W["positional_embedding"], add_period=n, pre_out=pre,
                         want_stats=save, out_dtype=f32)  # the residual stream is fp32
     x, mean0, rstd0 = r if save else (r, None, None)
     saved = TowerSaved() if save else None
-    cls_rows = torch.arange(B, device=image.device, dtype=i32) * n
     x = blocks_fwd(W, "transformer.", cfg.vision_layers, x, B, n, H, False, saved,
                    cls_rows if POOL_LAST_BLOCK else None)
     if POOL_LAST_BLOCK:
@@ -266,35 +276,30 @@ def vision_bwd(W, G, cfg, saved: TowerSaved, dfeat, on_layer_done=None):
 
 # ------------------------------------------------------------------------------------------------
 # clip.model.CLIP.encode_text
-def text_fwd(W, cfg, text, save: bool):
+def text_fwd(W, cfg, text, save: bool, rows=None):
+    """``rows``: static row count of the packed layout (>= sum of EOT position + 1; see PACK_TEXT); None lets
+    this function decide -- unpacked for small batches, else packed to the exact count (one host sync)."""
     B, S = text.shape
     d = cfg.transformer_width
     H = cfg.transformer_heads
     ids = text.to(i32).contiguous()
-    x, eot = O.embed_tokens_fwd(ids, W["token_embedding.weight"], W["positional_embedding"], out_dtype=f32)
     saved = TowerSaved() if save else None
-    cu = rows_src = None
-    if PACK_TEXT:  # keep positions 0 .. EOT of every caption only (see PACK_TEXT above)
-        pos_eot = eot - torch.arange(B, device=ids.device, dtype=i32) * S
-        cu = torch.zeros(B + 1, device=ids.device, dtype=i32)
-        cu[1:] = torch.cumsum(pos_eot + 1, 0)
-        keep = torch.arange(S, device=ids.device, dtype=i32)[None, :] <= pos_eot[:, None]
-        if PACK_ROWS_STATIC is None:
-            rows_src = keep.reshape(-1).nonzero().squeeze(1)  # int64 [sum(lengths)], host sync (dynamic shape)
-            x = x.index_select(0, rows_src)
-        else:  # static shapes: kept rows first (original order), then as many dropped rows as the bucket needs
-            order = torch.argsort((~keep).reshape(-1).to(torch.uint8), stable=True)
-            rows_src = order[:PACK_ROWS_STATIC].contiguous()
-            live = torch.arange(PACK_ROWS_STATIC, device=ids.device, dtype=i32) < cu[B]
-            x = x.index_select(0, rows_src) * live[:, None].to(x.dtype)   # surplus rows are all-zero
-        eot = (cu[1:] - 1).contiguous()                       # the EOT rows of the packed layout
+    cu = None
+    if PACK_TEXT and S <= 128 and (rows is not None or B * S >= PACK_MIN_ROWS):
+        # keep positions 0 .. EOT of every caption only
+        cu, eot = O.text_pack_plan(ids, rows if rows is not None else B * S)
+        if rows is None:
+            rows = max(1, int(cu[B].item()))   # dynamic shape: host sync
+        x = O.embed_tokens_packed_fwd(ids, W["token_embedding.weight"], W["positional_embedding"], cu, rows, out_dtype=f32)
+    else:
+        x, eot = O.embed_tokens_fwd(ids, W["token_embedding.weight"], W["positional_embedding"], out_dtype=f32)
     x = blocks_fwd(W, "transformer.", cfg.transformer_layers, x, B, S, H, True, saved,
                    eot if POOL_LAST_BLOCK else None, cu)
     if POOL_LAST_BLOCK:
         eot = None  # x is already [B, d]: the EOT tokens
     feat, head = _pool_project_fwd(W, x, eot, "ln_final.weight", "ln_final.bias", "text_projection", save)
     if save:
-        saved.extra = dict(B=B, S=S, ids=ids, eot=eot, x_last=x, head=head, cu=cu, rows_src=rows_src)
+        saved.extra = dict(B=B, S=S, ids=ids, eot=eot, x_last=x, head=head, cu=cu)
     return feat, saved
 
 
@@ -306,9 +311,10 @@ def text_bwd(W, G, cfg, saved: TowerSaved, dfeat, on_layer_done=None):
     dx = _pool_project_bwd(W, G, dfeat, e["x_last"], e["eot"], "ln_final.weight", "ln_final.bias", "text_projection",
                            pooled, mean, rstd)
     dx = blocks_bwd(W, G, "transformer.", cfg.transformer_layers, dx, B, S, H, True, saved, on_layer_done, e.get("cu"))
-    if e.get("rows_src") is not None:  # packed rows -> [B*S, d]; the dropped positions have zero gradient
-        dx = torch.zeros((B * S, dx.shape[1]), device=dx.device, dtype=bf16).index_copy_(0, e["rows_src"], dx)
-    O.embed_tokens_bwd(e["ids"], dx, G["token_embedding.weight"], G["positional_embedding"])
+    if e.get("cu") is not None:  # packed rows; the dropped positions have zero gradient
+        O.embed_tokens_packed_bwd(e["ids"], dx, e["cu"], G["token_embedding.weight"], G["positional_embedding"])
+    else:
+        O.embed_tokens_bwd(e["ids"], dx, G["token_embedding.weight"], G["positional_embedding"])
 
 
 # ------------------------------------------------------------------------------------------------

@@ -227,12 +227,15 @@ class ClipTrainer:
         self._hyper_live = False  # True while a CUDA-graph capture / warm-up wants device-side lr
         # CUDA-graph mode (enable_cuda_graph): step-dependent scalars live in device memory
         self._use_graph = False
-        self._graph = None
-        self._graph_key = None
         self._hyper = torch.zeros(3, device=self.device, dtype=f32)
         self._hyper_host = torch.zeros((64, 3), dtype=f32).pin_memory() if self.device.type == "cuda" else None
         self._hyper_slot = 0
         self._hyper_events = [None] * 64
+        self._rows_hint = None
+        self._rows_cache = {}
+        self._graphs = {}        # (input shapes / dtypes, packed text rows) -> captured step
+        self._static_in = {}     # input shapes / dtypes -> static input buffers shared by those graphs
+        self._graph_pool = None
         # Parameters that are not views of the bf16 shadow go stale when this trainer updates the weights;
         # CLIP.state_dict() calls write_back() while `dirty` (CLIP/train.py:210-216 saves model.state_dict()).
         import weakref
@@ -247,9 +250,7 @@ class ClipTrainer:
         small (strong scaling at 8 GPUs)."""
         self._use_graph = bool(on)
         if not on:
-            self._graph = None
-            if hasattr(self, "_packed_graphs"):
-                self._packed_graphs = {}
+            self._graphs, self._static_in, self._graph_pool = {}, {}, None
         return self
 
     def current_lr(self):
@@ -261,7 +262,32 @@ class ClipTrainer:
             return self.lr * max(0.0, (self.total_steps - s) / max(1, self.total_steps - self.warmup_steps))
         return self.lr
 
-    def forward_backward(self, image, text, fused_update=False):
+    def text_rows(self, text):
+        """Static row count of the packed text tower for this batch (towers.PACK_TEXT), or None when the tower
+        runs unpacked: the real count sum(EOT position + 1) rounded up to a bucket (~3 % of B x 77), so that a
+        handful of CUDA graphs covers every batch.  The count comes from the host copy of the tokens when
+        ``step_from_host`` has seen one, from a small cache keyed by the token tensor's identity and version
+        for device-resident batches that are fed repeatedly, and otherwise costs one host sync."""
+        B, S = text.shape
+        if not T.PACK_TEXT or S > 128 or B * S < T.PACK_MIN_ROWS:
+            return None
+        hint, self._rows_hint = self._rows_hint, None
+        if hint is None:
+            # the cache holds a reference to the tensor: its address cannot be recycled for other tokens while the
+            # entry lives, and the version counter catches in-place edits
+            key = (text.data_ptr(), text._version, tuple(text.shape), text.stride(), text.dtype)
+            hit = self._rows_cache.get(key)
+            if hit is None:
+                hint = int((text.argmax(-1) + 1).sum().item())
+                if len(self._rows_cache) >= 8:
+                    self._rows_cache.pop(next(iter(self._rows_cache)))
+                self._rows_cache[key] = (hint, text)
+            else:
+                hint = hit[0]
+        g = max(256, -(-(B * S // 32) // 256) * 256)
+        return min(B * S, -(-hint // g) * g)
+
+    def forward_backward(self, image, text, fused_update=False, text_rows="auto"):
         """Fills the flat gradient buffers with d(global loss)/d(params); returns the loss tensor.
         ``fused_update`` (used by ``step``): with a sharded optimiser each tower's gradient
         reduce-scatter, AdamW on the local shard and weight all-gather are issued on the tower's own
@@ -288,8 +314,10 @@ class ClipTrainer:
             sv = stt = main
         with torch.cuda.stream(sv):
             img_f, saved_i = T.vision_fwd(Wv, cfg, image, True)
+        if text_rows == "auto":
+            text_rows = self.text_rows(text)
         with torch.cuda.stream(stt):
-            txt_f, saved_t = T.text_fwd(Wt, cfg, text, True)
+            txt_f, saved_t = T.text_fwd(Wt, cfg, text, True, rows=text_rows)
         if two:
             main.wait_stream(sv)
             main.wait_stream(stt)
@@ -411,44 +439,48 @@ class ClipTrainer:
             out += [self.master[k], self.m[k], self.v[k], self.stores[k].w]
         return out
 
-    def _capture(self, image, text, pool=None):
+    def _capture(self, g_img, g_txt, rows, warm):
+        """Captures one step on the static inputs (g_img, g_txt) with `rows` packed text rows.  All graphs of
+        a trainer share one memory pool (they never run concurrently).  ``warm``: first capture for this
+        input shape -- run two eager steps before (and undo them)."""
         dev = self.device
-        self._g_img = image.detach().clone()
-        self._g_txt = text.detach().clone()
-        # warm-up on a side stream (allocator / NCCL / lazy module loading), then restore the state
-        backup = [t.clone() for t in self._state_tensors()]
-        count = self.step_count
-        side = torch.cuda.Stream(device=dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        try:  # whatever happens (a failed warm-up or capture falls back to eager), the optimiser state is restored
-            with torch.cuda.stream(side):
-                for _ in range(2):
-                    self.step_count += 1
-                    self._push_hyper()
-                    self._hyper_live = True
-                    self.forward_backward(self._g_img, self._g_txt, fused_update=True)
-                    self.optimizer_step(hyper=self._hyper, towers=not self.sharded, _count=False)
-                    self._hyper_live = False
-            torch.cuda.current_stream(dev).wait_stream(side)
-            torch.cuda.synchronize(dev)
-        finally:
-            self._hyper_live = False
-            with torch.no_grad():
-                for t, b in zip(self._state_tensors(), backup):
-                    t.copy_(b)
-                self.model.logit_scale.copy_(self.ls_master.reshape(()))
-            self.step_count = count
-            del backup
-        backup = [t.clone() for t in self._state_tensors()]   # a capture that dies half-way may have run nothing,
-        graph = torch.cuda.CUDAGraph()                         # but restore anyway: capture must be side-effect free
+        if self._graph_pool is None:
+            self._graph_pool = torch.cuda.graph_pool_handle()
+        if warm:
+            # warm-up on a side stream (allocator / NCCL / lazy module loading / per-shape index caches), then restore the state
+            backup = [t.clone() for t in self._state_tensors()]
+            count = self.step_count
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            try:  # whatever happens (a failed warm-up falls back to eager), the optimiser state is restored
+                with torch.cuda.stream(side):
+                    for _ in range(2):
+                        self.step_count += 1
+                        self._push_hyper()
+                        self._hyper_live = True
+                        self.forward_backward(g_img, g_txt, fused_update=True, text_rows=rows)
+                        self.optimizer_step(hyper=self._hyper, towers=not self.sharded, _count=False)
+                        self._hyper_live = False
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+            finally:
+                self._hyper_live = False
+                with torch.no_grad():
+                    for t, b in zip(self._state_tensors(), backup):
+                        t.copy_(b)
+                    self.model.logit_scale.copy_(self.ls_master.reshape(()))
+                self.step_count = count
+                del backup
+        backup = [t.clone() for t in self._state_tensors()]   # capture must be side-effect free even if it dies
+        graph = torch.cuda.CUDAGraph()
         try:
-            with (torch.cuda.graph(graph) if pool is None else torch.cuda.graph(graph, pool=pool)):
+            with torch.cuda.graph(graph, pool=self._graph_pool):
                 self._hyper_live = True
-                loss = self.forward_backward(self._g_img, self._g_txt, fused_update=True)
+                loss = self.forward_backward(g_img, g_txt, fused_update=True, text_rows=rows)
                 self.optimizer_step(hyper=self._hyper, towers=not self.sharded, _count=False)
                 self._hyper_live = False
-                self._g_loss = loss.reshape(1).clone()
-                self._g_correct = self.last_correct.reshape(1).clone()
+                g_loss = loss.reshape(1).clone()
+                g_correct = self.last_correct.reshape(1).clone()
         except Exception:
             self._hyper_live = False
             torch.cuda.synchronize(dev)
@@ -458,59 +490,30 @@ class ClipTrainer:
             raise
         finally:
             del backup
-        self._graph = graph
-        self._graph_key = (tuple(image.shape), image.dtype, tuple(text.shape), text.dtype)
+        return graph, g_loss, g_correct
 
     def _graph_step(self, image, text):
-        key = (tuple(image.shape), image.dtype, tuple(text.shape), text.dtype)
-        if self._graph is None or self._graph_key != key:
+        rows = self.text_rows(text)
+        in_key = (tuple(image.shape), image.dtype, tuple(text.shape), text.dtype)
+        static = self._static_in.get(in_key)
+        warm = static is None
+        if static is None:
+            static = self._static_in[in_key] = (image.detach().clone(), text.detach().clone())
+        g_img, g_txt = static
+        g_img.copy_(image, non_blocking=True)
+        g_txt.copy_(text, non_blocking=True)
+        entry = self._graphs.get((in_key, rows))
+        if entry is None:
             try:
-                self._capture(image, text)
+                entry = self._graphs[(in_key, rows)] = self._capture(g_img, g_txt, rows, warm)
             except Exception as e:  # capture is an optimisation: fall back to eager launches
                 import warnings
                 warnings.warn(f"CUDA-graph capture of the training step failed ({e!r}); running eagerly")
-                self._use_graph, self._graph, self._hyper_live = False, None, False
+                self.enable_cuda_graph(False)
+                self._hyper_live = False
+                self._rows_hint = rows
                 return self.step(image, text)
-        self._g_img.copy_(image, non_blocking=True)
-        self._g_txt.copy_(text, non_blocking=True)
-        self.step_count += 1
-        self._push_hyper()
-        self._graph.replay()
-        self.last_correct = self._g_correct[0]
-        return self._g_loss[0]
-
-    # -- packed text tower + CUDA graphs (B200CLIP_PACK_TEXT=2; NOT yet run on hardware) ----------------------
-    def _packed_rows(self, text):
-        """Rows of the packed text tower for this batch = sum over captions of (EOT position + 1).
-        step_from_host leaves the figure computed from the HOST tokens; device tokens cost one sync."""
-        hint, self._rows_hint = getattr(self, "_rows_hint", None), None
-        return hint if hint is not None else int((text.argmax(-1).long() + 1).sum().item())
-
-    def _packed_graph_step(self, image, text, bucket_rows=2048):
-        """One CUDA graph per row-count bucket (all buckets share one memory pool; they never run
-        concurrently).  Inside a graph the packed tensors have exactly `bucket` rows; the surplus rows
-        are zero and inert (towers.PACK_ROWS_STATIC)."""
-        B, S = text.shape
-        rows = self._packed_rows(text)
-        bucket = min(B * S, -(-rows // bucket_rows) * bucket_rows)
-        key = (tuple(image.shape), image.dtype, tuple(text.shape), text.dtype, bucket)
-        if not hasattr(self, "_packed_graphs"):
-            self._packed_graphs, self._graph_pool = {}, torch.cuda.graph_pool_handle()
-        entry = self._packed_graphs.get(key)
-        if entry is None:
-            keep = (self._graph, self._graph_key, getattr(self, "_g_img", None), getattr(self, "_g_txt", None),
-                    getattr(self, "_g_loss", None), getattr(self, "_g_correct", None))
-            T.PACK_ROWS_STATIC = bucket
-            try:
-                self._capture(image, text, pool=self._graph_pool)
-                entry = (self._graph, self._g_img, self._g_txt, self._g_loss, self._g_correct)
-            finally:
-                T.PACK_ROWS_STATIC = None
-                (self._graph, self._graph_key, self._g_img, self._g_txt, self._g_loss, self._g_correct) = keep
-            self._packed_graphs[key] = entry
-        graph, g_img, g_txt, g_loss, g_correct = entry
-        g_img.copy_(image, non_blocking=True)
-        g_txt.copy_(text, non_blocking=True)
+        graph, g_loss, g_correct = entry
         self.step_count += 1
         self._push_hyper()
         graph.replay()
@@ -568,8 +571,8 @@ class ClipTrainer:
         cur.wait_event(ev)
         img_d.record_stream(cur)
         txt_d.record_stream(cur)
-        if T.PACK_STATIC:  # row count of the packed text tower from the host copy of the tokens: no device sync
-            self._rows_hint = int((text_host.argmax(-1).long() + 1).sum())
+        if T.PACK_TEXT:  # row count of the packed text tower from the host copy of the tokens: no device sync
+            self._rows_hint = int((text_host.argmax(-1) + 1).sum())
         # enqueue this step's GPU work FIRST: cudaMemcpyAsync of a large pinned batch can hold the host
         # thread for about the DMA time (measured 1.9 ms for 77 MB, more when copies queue up), and that
         # must not delay the launch of the step the GPU is waiting for
@@ -584,11 +587,8 @@ class ClipTrainer:
         """One optimisation step on this rank's slice (image [Bl,3,R,R], text [Bl,77]) of the
         global batch; returns the global mean loss as a device tensor (no host sync)."""
         self.dirty = self._has_unlinked
-        if self._use_graph and not T.PACK_TEXT:
+        if self._use_graph:   # one graph per (input shape, packed-text row bucket)
             return self._graph_step(image, text)
-        if self._use_graph and T.PACK_STATIC:   # packed text with static (bucketed) shapes: one graph per bucket
-            return self._packed_graph_step(image, text)
-        # (packed text, B200CLIP_PACK_TEXT=1: data-dependent row count -> eager launches)
         self.step_count += 1
         loss = self.forward_backward(image, text, fused_update=True)
         self.optimizer_step(towers=not self.sharded, _count=False)

@@ -138,6 +138,7 @@ int b200clip_attn_bwd(b200clip_ctx* ctx, const void* qkv, const void* out, const
  * indexed [row * H + head].  With upstream's causal mask nothing after a caption's EOT token can reach
  * its pooled feature (clip/model.py: build_attention_mask + x[arange, text.argmax(-1)]), so those
  * positions need not exist at all: pack each caption to EOT + 1 tokens. */
+/* Rows cu[B] .. total_rows-1 of out / dqkv (surplus of a static row count) are zero-filled by the kernels. */
 int b200clip_attn_fwd_varlen(b200clip_ctx* ctx, const void* qkv, void* out, float* lse, const int32_t* cu, int64_t B,
                              int64_t S_max, int64_t H, int64_t total_rows, int causal, void* stream);
 int b200clip_attn_bwd_varlen(b200clip_ctx* ctx, const void* qkv, const void* out, const float* lse, const void* dout,
@@ -153,6 +154,36 @@ int b200clip_embed_tokens_fwd(b200clip_ctx* ctx, const int32_t* ids, const void*
 /* dtable fp32 [V,d] and dpos fp32 [S,d] are ACCUMULATED into (atomics). */
 int b200clip_embed_tokens_bwd(b200clip_ctx* ctx, const int32_t* ids, const void* dout, float* dtable, float* dpos,
                               int64_t B, int64_t S, int64_t d, int64_t vocab, void* stream);
+
+/* ---- packed text tower -------------------------------------------------------------------------------
+ * Under upstream's causal mask (clip/model.py: build_attention_mask) nothing after a caption's EOT token can
+ * reach the pooled feature x[arange, text.argmax(-1)], and those positions receive exactly-zero gradients:
+ * caption b keeps len_b = argmax_s ids[b,s] + 1 rows, stored back to back.
+ * text_pack_plan: cu int32 [B+1] = exclusive prefix sum of len (cu[0] = 0), eot_row int32 [B] = cu[b+1]-1 (the
+ * row upstream pools at, in the packed layout).  rows_cap = rows of the caller's packed buffers (>= cu[B]
+ * expected; cu is clamped to it so that a too-small buffer truncates captions instead of corrupting memory). */
+int b200clip_text_pack_plan(b200clip_ctx* ctx, const int32_t* ids, int32_t* cu, int32_t* eot_row, int64_t B, int64_t S,
+                            int64_t rows_cap, void* stream);
+/* embed_tokens_fwd into the packed layout: out [rows_total, d]; rows cu[B] .. rows_total-1 (the surplus of a
+ * static, CUDA-graph friendly row count) are zero-filled.  The packed attention kernels zero-fill the same
+ * rows of their outputs, so every later row-wise kernel maps finite zeros to finite values there and the
+ * backward keeps them exactly zero. */
+int b200clip_embed_tokens_packed_fwd(b200clip_ctx* ctx, const int32_t* ids, const void* table, const void* pos,
+                                     const int32_t* cu, void* out, int out_dtype, int64_t B, int64_t S, int64_t d,
+                                     int64_t vocab, int64_t rows_total, void* stream);
+/* embed_tokens_bwd reading dout bf16 [rows_total, d] in the packed layout. */
+int b200clip_embed_tokens_packed_bwd(b200clip_ctx* ctx, const int32_t* ids, const void* dout, const int32_t* cu,
+                                     float* dtable, float* dpos, int64_t B, int64_t S, int64_t d, int64_t vocab,
+                                     void* stream);
+
+/* ---- row gather / scatter (x[:, 0, :], x[arange, argmax] of the LAST block: only the pooled token's
+ * out_proj / ln_2 / MLP is live) --------------------------------------------------------------------------
+ * gather: dst[i,:] = src[idx[i],:] for i < n (rows of row_bytes, a multiple of 16; src pitch src_ld_bytes).
+ * scatter: dst[idx[i],:] = src[i,:]; zero_first != 0 clears dst [dst_rows, row_bytes] before. */
+int b200clip_gather_rows(b200clip_ctx* ctx, const void* src, int64_t src_ld_bytes, const int32_t* idx, void* dst,
+                         int64_t n, int64_t row_bytes, void* stream);
+int b200clip_scatter_rows(b200clip_ctx* ctx, const void* src, const int32_t* idx, void* dst, int64_t dst_rows,
+                          int64_t n, int64_t row_bytes, int zero_first, void* stream);
 
 /* ---- visual.conv1 (Conv2d, kernel = stride = patch, no bias) as im2col + GEMM ---------------------
  * image: [B,3,R,R] bf16 or fp32 (in_dtype) -> cols bf16 [B*g*g, ldcols], ldcols >= 3*p*p (padded

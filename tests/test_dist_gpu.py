@@ -10,11 +10,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("world", [2])
+@pytest.mark.parametrize("world", [2, 8])
 def test_sharded_step_matches_single_device(world):
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
-           "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tools", "dist_check.py")]
+           "--master-addr", "127.0.0.1", "--master-port", str(29531 + world), os.path.join(ROOT, "tools", "dist_check.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert r.returncode == 0 and "RESULT=PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -1,8 +1,13 @@
-"""Multi-GPU parity check (run under torchrun): the R-rank sharded step must equal the
-single-device step on the concatenated global batch (loss within 1e-3 relative, gradients equal
-up to reduction order)."""
+"""Multi-GPU parity check (run under torchrun): the R-rank sharded step must equal (a) the CPU ORACLE's
+autograd on the concatenated global batch (loss within 1e-3 relative, every parameter gradient cosine
+>= 0.99 / norm within 5 %, the single-GPU tolerances) and (b) the single-device CUDA step (gradients equal
+up to reduction order).  Captions have ragged lengths U{3..76} and the packed text tower is forced on
+(B200CLIP_PACK_MIN_ROWS=0) unless the caller exports another value.
+  DIST_BATCH (global pairs, default 8 x world), DIST_MODEL, DIST_GRAPH=0 to skip the graph leg."""
 import os
 import sys
+
+os.environ.setdefault("B200CLIP_PACK_MIN_ROWS", "0")
 
 import torch
 import torch.distributed as dist
@@ -22,11 +27,11 @@ def main():
     from construction_clip_b200.train import ClipTrainer, clip_contrastive_loss
 
     name = os.environ.get("DIST_MODEL", "ViT-B/32")
-    Bg = int(os.environ.get("DIST_BATCH", "16"))
+    Bg = int(os.environ.get("DIST_BATCH", str(max(16, 8 * world))))
     cfg = O.CONFIGS[name]
     orc = oracle_model(name)
     img = O.synth_images(Bg, cfg.image_resolution, seed=SEED)
-    tok = O.synth_tokens(Bg, seed=SEED, min_len=3, max_len=20)
+    tok = O.synth_tokens(Bg, seed=SEED, min_len=3, max_len=76)
     bl = Bg // world
     sl = slice(rank * bl, (rank + 1) * bl)
 
@@ -55,6 +60,34 @@ def main():
     rel = abs(loss.item() - loss1.item()) / abs(loss1.item())
     if rel > 1e-3:
         ok = False
+    # (a) against the oracle's autograd on the concatenated batch (rank 0 only: the host cores are shared)
+    orel, ocos = 0.0, 1.0
+    if rank == 0:
+        torch.set_num_threads(max(1, (os.cpu_count() or 8) // 2))
+        lpi, lpt = orc(img, tok)
+        oloss = O.clip_loss(lpi, lpt)
+        oloss.backward()
+        orel = abs(loss.item() - oloss.item()) / abs(oloss.item())
+        if orel > 1e-3:
+            ok = False
+            print(f"oracle loss mismatch: {loss.item()} vs {oloss.item()}", flush=True)
+        ref = dict(orc.named_parameters())
+        for k, pre in (("visual", "visual."), ("text", "")):
+            views = tr.stores[k].grad_views(flat_sharded[k])
+            for n, v in views.items():
+                g = ref[pre + n].grad
+                got = v.float().cpu()
+                if got.numel() != g.numel():           # zero-padded conv1.weight
+                    got = got[:, :g[0].numel()]
+                got = got.reshape(g.shape)
+                gn = g.double().norm().item()
+                if gn < 1e-7:
+                    continue
+                c = cosine(got, g)
+                ocos = min(ocos, c)
+                if c < 0.99 or abs(got.double().norm().item() - gn) > 0.05 * gn:
+                    ok = False
+                    print(f"oracle grad mismatch {pre + n}: cos {c:.4f} norm {got.norm().item():.3e} vs {gn:.3e}", flush=True)
     worst = 1.0
     for k in flat_sharded:
         c = cosine(flat_sharded[k], tr1.grads[k])
@@ -122,7 +155,9 @@ def main():
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"DIST_CHECK world={world} Bg={Bg} loss_sharded={loss.item():.6f} loss_single={loss1.item():.6f} rel={rel:.2e} "
+        print(f"DIST_CHECK world={world} Bg={Bg} packed_text={T.T.PACK_TEXT and bl * 77 >= T.T.PACK_MIN_ROWS} "
+              f"oracle_loss_rel={orel:.2e} oracle_worst_grad_cos={ocos:.6f} "
+              f"loss_sharded={loss.item():.6f} loss_single={loss1.item():.6f} rel={rel:.2e} "
               f"worst_grad_cos={worst:.6f} dls_rel={dls:.2e} autograd_cos={c2:.6f} replicas_identical={same} "
               f"graph_vs_eager_loss={gb:.5f}/{ga:.5f} sharded_vs_replicated_maxdiff={shard_diff:.2e} "
               f"RESULT={'PASS' if flag.item() == 1.0 else 'FAIL'}", flush=True)

@@ -1,0 +1,26 @@
+#!/bin/bash
+# One gpurun call = a list of stages, each under its own timeout, each logging to gpurun_out/<tag>_<stage>.log.
+#   tools/gpu_call.sh <tag> stage1 stage2 ...      stages: tests | bench | bench_nopack | gemm | gemm128 | micro | infer
+set -u
+TAG=$1; shift
+mkdir -p gpurun_out
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.limit --format=csv > gpurun_out/${TAG}_gpu.txt 2>&1
+for STAGE in "$@"; do
+    T0=$(date +%s)
+    case $STAGE in
+        tests)        timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 > gpurun_out/${TAG}_tests.log 2>&1 ;;
+        tests_all)    timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/${TAG}_tests.log 2>&1 ;;
+        bench)        timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
+        bench_nopack) B200CLIP_PACK_TEXT=0 B200CLIP_BENCH_VARIANTS=0 timeout 400 python bench.py --steps 5 > gpurun_out/${TAG}_bench_nopack.json 2> gpurun_out/${TAG}_bench_nopack.err ;;
+        bench128)     B200CLIP_BENCH_VARIANTS=0 BENCH_GLOBAL_BATCH=128 timeout 400 python bench.py --steps 20 > gpurun_out/${TAG}_bench128.json 2> gpurun_out/${TAG}_bench128.err ;;
+        gemm)         timeout 300 python tools/gemm_bench.py 1024 > gpurun_out/${TAG}_gemm1024.txt 2>&1 ;;
+        gemm128)      timeout 300 python tools/gemm_bench.py 128 > gpurun_out/${TAG}_gemm128.txt 2>&1 ;;
+        micro)        timeout 300 python tools/ncu_micro.py --time > gpurun_out/${TAG}_micro.txt 2>&1 ;;
+        infer)        timeout 400 python tools/infer_bench.py > gpurun_out/${TAG}_infer.txt 2>&1 ;;
+        smoke)        timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1 ;;
+        *)            echo "unknown stage $STAGE" ;;
+    esac
+    echo "stage $STAGE rc=$? $(( $(date +%s) - T0 ))s"
+done
+tail -3 gpurun_out/${TAG}_tests.log 2>/dev/null
+cut -c1-400 gpurun_out/${TAG}_bench.json 2>/dev/null
