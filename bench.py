@@ -162,7 +162,23 @@ def torch_eager_bf16_rate(model_name, pairs, steps, warmup, dev):
     import torch
     from oracle import clip_oracle as ORC
     cfg = ORC.CONFIGS[model_name]
-    model = ORC.build(model_name, seed=SEED).to(dev).to(torch.bfloat16).train()
+    model = ORC.build(model_name, seed=SEED).to(dev).train()
+
+    def _convert(l):   # upstream clip.model.convert_weights with bf16 for fp16: LayerNorm and embeddings stay fp32
+        if isinstance(l, (torch.nn.Conv2d, torch.nn.Linear)):
+            l.weight.data = l.weight.data.to(torch.bfloat16)
+            if l.bias is not None:
+                l.bias.data = l.bias.data.to(torch.bfloat16)
+        if isinstance(l, torch.nn.MultiheadAttention):
+            for attr in ("in_proj_weight", "in_proj_bias"):
+                t = getattr(l, attr)
+                if t is not None:
+                    t.data = t.data.to(torch.bfloat16)
+        for name in ("text_projection", "proj"):
+            if hasattr(l, name) and getattr(l, name) is not None:
+                getattr(l, name).data = getattr(l, name).data.to(torch.bfloat16)
+
+    model.apply(_convert)
     opt = torch.optim.AdamW(model.parameters(), lr=1e-5, eps=1e-6, weight_decay=0.0, fused=True)
     img = ORC.synth_images(pairs, cfg.image_resolution, seed=SEED).to(dev).to(torch.bfloat16)
     tok = ORC.synth_tokens(pairs, seed=SEED).to(dev)
@@ -435,6 +451,200 @@ def run_ours(args):
     shutdown()
 
 
+# ------------------------------------------------------------------------------------------------
+# Secondary modes: the other BASELINE.json configs (`--config 1|3|4|5`).  The headline stays config 2.
+SECONDARY = {
+    # config: (model, what one "step" is, units per step per GPU, unit name)
+    1: ("ViT-B/32", "model(image[32], text[16]) -> logits.softmax.argmax (CLIP/predict.py:40-54)", 32, "images/s"),
+    3: ("ViT-B/16", "encode_image on 4096 images per GPU in chunks of 1024 (parse_coco-style prefix extraction)", 4096, "images/s"),
+    4: ("ViT-L/14", "encode_image + encode_text at batch 512 per GPU", 512, "pairs/s"),
+    5: ("ViT-L/14@336px", "contrastive fine-tune step, 512 pairs per GPU (global 4096 on 8 GPUs), global fused logits/loss, "
+                          "activation recompute", 512, "pairs/s"),
+}
+
+
+def run_secondary(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the CLIP hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    from construction_clip_b200 import lib as L
+    from construction_clip_b200.model import CLIP, CONFIGS
+    from oracle import clip_oracle as ORC  # FLOP model + synthetic-input recipe + the config-1 CPU baseline
+
+    name, what, units, unit = SECONDARY[args.config]
+    cfg = CONFIGS[name]
+    torch.manual_seed(SEED)
+    model = CLIP(cfg).to(dev)
+    ls = model.logit_scale.data.float().clone()
+    model = model.to(torch.bfloat16)
+    model.logit_scale.data = ls
+    if world > 1:
+        for p in model.parameters():
+            dist.broadcast(p.data, 0)
+    R = cfg.image_resolution
+    bpg = int(os.environ.get("BENCH_PAIRS_PER_GPU", str(units)))   # tuning runs only; default = the BASELINE shape
+    trainer = None
+    if args.config == 1:
+        model.eval()
+        img_h = ORC.synth_images(32, R, seed=SEED).pin_memory()
+        tok_h = ORC.synth_tokens(16, seed=SEED, min_len=3, max_len=12).to(torch.int32).pin_memory()
+        img_d, tok_d = img_h.to(dev), tok_h.to(dev)
+        f_unit = (32 * ORC.flops_image(ORC.CONFIGS[name]) + 16 * ORC.flops_text(ORC.CONFIGS[name])) / 32
+        bpg = 32
+
+        def step_dev():
+            with torch.no_grad():
+                lpi, _ = model(img_d, tok_d)
+                return lpi.softmax(dim=-1).argmax(dim=1)
+
+        def step_host():
+            with torch.no_grad():
+                lpi, _ = model(img_h.to(dev, non_blocking=True), tok_h.to(dev, non_blocking=True))
+                return lpi.softmax(dim=-1).argmax(dim=1).cpu()
+        h2d, d2h = img_h.numel() * 4 + tok_h.numel() * 4, 32 * 8
+    elif args.config == 3:
+        model.eval()
+        chunk = min(1024, bpg)
+        img_h = ORC.synth_images(chunk, R, seed=SEED + rank).to(torch.bfloat16).pin_memory()
+        img_d = img_h.to(dev)
+        f_unit = ORC.flops_image(ORC.CONFIGS[name])
+
+        def step_dev():
+            with torch.no_grad():
+                return [model.encode_image(img_d) for _ in range(bpg // chunk)][-1]
+
+        def step_host():
+            with torch.no_grad():
+                return [model.encode_image(img_h.to(dev, non_blocking=True)).cpu() for _ in range(bpg // chunk)][-1]
+        h2d, d2h = (bpg // chunk) * img_h.numel() * 2, bpg * cfg.embed_dim * 2
+    elif args.config == 4:
+        model.eval()
+        img_h = ORC.synth_images(bpg, R, seed=SEED + rank).to(torch.bfloat16).pin_memory()
+        tok_h = ORC.synth_tokens(bpg, seed=SEED + rank).to(torch.int32).pin_memory()
+        img_d, tok_d = img_h.to(dev), tok_h.to(dev)
+        f_unit = ORC.flops_pair(ORC.CONFIGS[name])
+
+        def step_dev():
+            with torch.no_grad():
+                return model.encode_image(img_d), model.encode_text(tok_d)
+
+        def step_host():
+            with torch.no_grad():
+                a = model.encode_image(img_h.to(dev, non_blocking=True))
+                b = model.encode_text(tok_h.to(dev, non_blocking=True))
+                return a.cpu(), b.cpu()
+        h2d, d2h = img_h.numel() * 2 + tok_h.numel() * 4, 2 * bpg * cfg.embed_dim * 2
+    else:
+        from construction_clip_b200.train import ClipTrainer
+        model.train()
+        trainer = ClipTrainer(model, lr=1e-5, warmup_steps=5000, total_steps=100000, recompute=True)
+        img_h = ORC.synth_images(bpg, R, seed=SEED + 17 * rank).to(torch.bfloat16).pin_memory()
+        tok_h = ORC.synth_tokens(bpg, seed=SEED + 17 * rank).to(torch.int32).pin_memory()
+        img_d, tok_d = img_h.to(dev), tok_h.to(dev)
+        f_unit = 3.0 * ORC.flops_pair(ORC.CONFIGS[name])
+
+        def step_dev():
+            return trainer.step(img_d, tok_d)
+
+        def step_host():
+            return trainer.step_from_host(img_h, tok_h, next_batch=(img_h, tok_h))
+        h2d, d2h = img_h.numel() * 2 + tok_h.numel() * 4, 4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, out
+
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    n0 = L.launch_count()
+    ms, out = timed(step_dev, args.steps)
+    launches = L.launch_count() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step_host()
+    e2e_ms, _ = timed(step_host, args.steps)
+    torch.cuda.synchronize()
+    final = None
+    if args.config == 5:
+        final = float(out.item())
+    if rank == 0:
+        peaks = load_peaks()
+        value = world * bpg / (ms * 1e-3)
+        tf = value / world * f_unit / 1e12
+        cpu_baseline = None
+        if args.config == 1 and world == 1:   # BASELINE configs[0] is the reference's own CPU-runnable case
+            torch.set_num_threads(os.cpu_count() or 1)
+            orc = ORC.build(name, seed=SEED).eval()
+            ci, ct = ORC.synth_images(32, R, seed=SEED), ORC.synth_tokens(16, seed=SEED, min_len=3, max_len=12)
+            ts = []
+            with torch.no_grad():
+                for i in range(4):
+                    t0 = time.perf_counter()
+                    orc(ci, ct)[0].softmax(dim=-1).argmax(dim=1)
+                    ts.append(time.perf_counter() - t0)
+            sec = statistics.median(ts[1:])
+            cpu_baseline = {"value": 32 / sec, "unit": unit, "cores": torch.get_num_threads(), "kind": "port",
+                            "sample": f"oracle fp32 forward on the exact config-1 shapes, median of 3 after 1 warm-up ({sec:.3f} s/call)"}
+        emit({
+            "metric": f"BASELINE config {args.config}: {unit.split('/')[0]} per second", "value": value, "unit": unit,
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"BASELINE config {args.config} (secondary mode, not the headline): CLIP {name}, {what}; "
+                                   f"{bpg} per GPU, random-init weights seed {SEED}",
+                       "per_gpu_batch": bpg, "parallelism": f"dp{world}", "cuda_graph": False,
+                       "algorithmic_gflop_per_unit": f_unit / 1e9, "tflops_per_gpu": tf,
+                       "frac_of_bf16_burst_peak": tf / peaks["bf16_burst"],
+                       "frac_of_bf16_sustained_peak": tf / peaks["bf16_sustained"], "final_loss": final,
+                       "l2_policy": "activations exceed the 126 MB L2 (config 1: 3 warm-up calls, weights stay L2 resident as in "
+                                    "a real predict loop)"},
+            "e2e": {"value": world * bpg / (e2e_ms * 1e-3), "unit": unit, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms},
+            "gpu_launches": launches, "clocks": clocks,
+            "roofline": {"bound": "tensor", "achieved": tf, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
+                         "frac": tf / peaks["bf16_burst"], "traffic": None,
+                         "kernel": "whole path (tcgen05 GEMM family dominates); algorithmic FLOPs x rate",
+                         "peak_source": f"{peaks['source']} (burst cuBLAS bf16)"},
+            "cpu_baseline": cpu_baseline,
+        })
+    if world > 1:
+        if trainer is not None:
+            trainer.enable_cuda_graph(False)
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -442,10 +652,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--model", default="ViT-B/32")
+    ap.add_argument("--config", type=int, default=2, choices=[1, 2, 3, 4, 5],
+                    help="BASELINE.json config: 2 (default) = the headline train step; 1/3/4/5 = secondary modes")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
+    elif args.config != 2:
+        run_secondary(args)
     else:
         run_ours(args)
 

@@ -160,26 +160,24 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const T
                      const __nv_bfloat16* __restrict__ dres, int64_t lddres, __nv_bfloat16* __restrict__ dx,
                      int64_t lddx, float* __restrict__ dgamma, float* __restrict__ dbeta,
                      float* __restrict__ dx_colsum, int rows, int d) {
-    extern __shared__ __align__(128) uint8_t s_ln[];  // float acc[3][d] | bf16 gamma[d] | per warp: 2 stages x {x | dy | dres}
+    extern __shared__ __align__(128) uint8_t s_ln[];  // bf16 gamma[d] | per warp: 2 stages x {x | dy | dres}
     __shared__ uint64_t s_bar[kLnThreads / 32][2];
-    float* s_acc = reinterpret_cast<float*>(s_ln);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int wpb = blockDim.x >> 5;
     const int nunit = d >> 2;
     const uint32_t xb = static_cast<uint32_t>(d) * sizeof(TX), yb = static_cast<uint32_t>(d) * 2u;
     const uint32_t stage_bytes = xb + 2u * yb;
-    __nv_bfloat16* s_gamma = reinterpret_cast<__nv_bfloat16*>(s_ln + static_cast<size_t>(3) * d * sizeof(float));
-    uint8_t* wbase = s_ln + static_cast<size_t>(3) * d * sizeof(float) + yb + static_cast<size_t>(warp) * 2u * stage_bytes;
-    for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) s_acc[i] = 0.f;
-    griddep_launch_dependents();
-    griddep_wait();  // global memory from here on
-    for (int i = threadIdx.x; i < d; i += blockDim.x) s_gamma[i] = gamma[i];
-    if (lane == 0) {
+    __nv_bfloat16* s_gamma = reinterpret_cast<__nv_bfloat16*>(s_ln);
+    uint8_t* wbase0 = s_ln + yb;
+    uint8_t* wbase = wbase0 + static_cast<size_t>(warp) * 2u * stage_bytes;
+    if (lane == 0) {   // per-warp barriers: only this warp ever touches them
         mbar_init(&s_bar[warp][0], 1);
         mbar_init(&s_bar[warp][1], 1);
         fence_barrier_init();
     }
-    __syncthreads();
+    __syncwarp();
+    griddep_launch_dependents();
+    griddep_wait();  // global memory from here on
 
     auto issue = [&](int r, int stage) {  // lane 0
         const int64_t src = row_index ? row_index[r] : r;
@@ -203,11 +201,13 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const T
     const int stride = gridDim.x * wpb;
     int r = blockIdx.x * wpb + warp;
     float mu_n = 0.f, rs_n = 0.f;
-    if (r < rows) {
+    if (r < rows) {   // the first row is on its way before anything else touches global memory
         if (lane == 0) issue(r, 0);
         mu_n = mean[r];
         rs_n = rstd[r];
     }
+    for (int i = threadIdx.x; i < d; i += blockDim.x) s_gamma[i] = gamma[i];
+    __syncthreads();
     const float inv_d = 1.0f / d;
     for (uint32_t k = 0; r < rows; r += stride, ++k) {
         const uint32_t st = k & 1u;
@@ -275,28 +275,37 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int64_t lddy, const T
             }
         }
     }
+    // Column sums (dgamma, dbeta, dx_colsum).  Each warp parks its partial sums in its own pipeline buffers
+    // (idle now: every row it requested has been consumed; 2 stages >= 3*d floats), then the block adds the
+    // warps' partials column by column and issues ONE global atomic per column.  (Shared-memory fp32
+    // atomicAdd compiles to a compare-and-swap spin loop: 72 of them per thread with 8-way contention were
+    // the largest fixed cost of this kernel at small row counts.)
     if (dgamma != nullptr || COLSUM) {
+        float* wp = reinterpret_cast<float*>(wbase);
+        __syncwarp();
 #pragma unroll
         for (int m = 0; m < NU; ++m) {
             const int u = lane + 32 * m;
             if (u < nunit) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (dgamma != nullptr) {
-                        atomicAdd(&s_acc[u * 4 + j], ag[m][j]);
-                        atomicAdd(&s_acc[d + u * 4 + j], ab[m][j]);
-                    }
-                    if constexpr (COLSUM) atomicAdd(&s_acc[2 * d + u * 4 + j], ac[m][j]);
-                }
+                *reinterpret_cast<float4*>(wp + u * 4) = make_float4(ag[m][0], ag[m][1], ag[m][2], ag[m][3]);
+                *reinterpret_cast<float4*>(wp + d + u * 4) = make_float4(ab[m][0], ab[m][1], ab[m][2], ab[m][3]);
+                if constexpr (COLSUM)
+                    *reinterpret_cast<float4*>(wp + 2 * d + u * 4) = make_float4(ac[m][0], ac[m][1], ac[m][2], ac[m][3]);
             }
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < d; i += blockDim.x) {
-            if (dgamma != nullptr) {
-                atomicAdd(&dgamma[i], s_acc[i]);
-                atomicAdd(&dbeta[i], s_acc[d + i]);
+        const int ncol = (COLSUM ? 3 : 2) * d;
+        for (int i = threadIdx.x; i < ncol; i += blockDim.x) {
+            float t = 0.f;
+            for (int w = 0; w < wpb; ++w)
+                t += reinterpret_cast<const float*>(wbase0 + static_cast<size_t>(w) * 2u * stage_bytes)[i];
+            if (i < d) {
+                if (dgamma != nullptr) atomicAdd(&dgamma[i], t);
+            } else if (i < 2 * d) {
+                if (dgamma != nullptr) atomicAdd(&dbeta[i - d], t);
+            } else {
+                atomicAdd(&dx_colsum[i - 2 * d], t);
             }
-            if constexpr (COLSUM) atomicAdd(&dx_colsum[i], s_acc[2 * d + i]);
         }
     }
 }
@@ -392,10 +401,10 @@ extern "C" int b200clip_layernorm_bwd(b200clip_ctx* ctx, const void* dy, int64_t
                      reinterpret_cast<uintptr_t>(dres) | reinterpret_cast<uintptr_t>(gamma)) & 15) == 0,
                    "layernorm_bwd: pointers must be 16-byte aligned");
     B200_CHECK_ARG(x_dtype == B200CLIP_DT_BF16 || x_dtype == B200CLIP_DT_F32, "layernorm_bwd: bad x dtype");
-    // shared memory: 3 column accumulators, gamma, and per warp two stages of {x row, dy row, dres row}
+    // shared memory: gamma, and per warp two stages of {x row, dy row, dres row} (reused for the column sums)
     const size_t xsz = x_dtype == B200CLIP_DT_F32 ? 4 : 2;
     const size_t stage = static_cast<size_t>(d) * (xsz + 4);
-    const size_t fixed = static_cast<size_t>(d) * (3 * sizeof(float) + 2);
+    const size_t fixed = static_cast<size_t>(d) * 2;
     int wpb = kLnThreads / 32;
     while (wpb > 1 && fixed + wpb * 2 * stage > 200 * 1024) wpb >>= 1;
     const size_t smem = fixed + wpb * 2 * stage;

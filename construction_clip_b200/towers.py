@@ -66,6 +66,7 @@ class BlockSaved:
 class TowerSaved:
     blocks: list = field(default_factory=list)
     extra: dict = field(default_factory=dict)
+    recompute: bool = False   # keep block inputs only; blocks_bwd re-runs each block's forward (see blocks_fwd)
 
 
 def _blk(prefix: str, i: int) -> str:
@@ -74,6 +75,31 @@ def _blk(prefix: str, i: int) -> str:
 
 # ------------------------------------------------------------------------------------------------
 # clip.model.ResidualAttentionBlock:  x = x + attn(ln_1(x)) ; x = x + c_proj(QuickGELU(c_fc(ln_2(x))))
+def _block_fwd(W, p, x, B, S, H, causal, save, cu=None):
+    """One residual block on every token -> (y fp32, BlockSaved or None)."""
+    if save:
+        h1, mean1, rstd1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"], want_stats=True)
+    else:
+        h1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"])
+    qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
+    if save:
+        a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True, cu=cu)
+    else:
+        a, lse = O.attn_fwd(qkv, B, S, H, causal, cu=cu), None
+    x2 = O.linear_fwd(a, W[p + "attn.out_proj.weight"], W[p + "attn.out_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x,
+                      out_dtype=f32)
+    if save:
+        h2, mean2, rstd2 = O.layernorm_fwd(x2, W[p + "ln_2.weight"], W[p + "ln_2.bias"], want_stats=True)
+        f = torch.empty((x.shape[0], 4 * x.shape[1]), device=x.device, dtype=bf16)
+    else:
+        h2 = O.layernorm_fwd(x2, W[p + "ln_2.weight"], W[p + "ln_2.bias"])
+        f = None
+    g = O.linear_fwd(h2, W[p + "mlp.c_fc.weight"], W[p + "mlp.c_fc.bias"], epilogue=L.EPI_QUICKGELU, preact=f)
+    y = O.linear_fwd(g, W[p + "mlp.c_proj.weight"], W[p + "mlp.c_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x2,
+                     out_dtype=f32)
+    return y, (BlockSaved(x, mean1, rstd1, h1, qkv, a, lse, x2, mean2, rstd2, h2, f, g) if save else None)
+
+
 def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None, pool_rows=None, cu=None):
     """``pool_rows`` (int32 [B], rows of ``x``): the only tokens of the LAST block's output that the
     tower uses (CLS rows for ``visual``: ``x[:, 0, :]``; EOT rows for text: ``x[arange, argmax]``).
@@ -81,34 +107,23 @@ def blocks_fwd(W, prefix, layers, x, B, S, H, causal, saved: TowerSaved | None, 
     MLP outputs are dead for all other tokens (upstream computes and discards them), and so are the
     corresponding gradients (exactly zero).  With ``pool_rows`` the last block runs those three
     operators on the B pooled rows only and returns ``[B, d]`` -- same features, same gradients,
-    18/24 of the last block's GEMM work less (6 % of a 12-layer tower, forward and backward)."""
+    18/24 of the last block's GEMM work less (6 % of a 12-layer tower, forward and backward).
+
+    ``saved.recompute`` (activation recompute, BASELINE config 5: ViT-L/14@336px at 512 pairs / GPU would keep
+    255 GB of activations): a block keeps only its INPUT (fp32 residual stream, 4 bytes x d per token) and
+    blocks_bwd re-runs its forward right before its backward -- one extra forward of arithmetic, 1/9 of the
+    memory.  The algorithmic FLOP count of a step does not change."""
     for i in range(layers):
         p = _blk(prefix, i)
-        save = saved is not None
         if pool_rows is not None and i == layers - 1:
             return _last_block_fwd(W, p, x, B, S, H, causal, saved, pool_rows, cu)
-        if save:
-            h1, mean1, rstd1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"], want_stats=True)
+        if saved is not None and saved.recompute:
+            y, _ = _block_fwd(W, p, x, B, S, H, causal, False, cu)
+            saved.blocks.append(BlockSaved(x=x))
         else:
-            h1 = O.layernorm_fwd(x, W[p + "ln_1.weight"], W[p + "ln_1.bias"])
-        qkv = O.linear_fwd(h1, W[p + "attn.in_proj_weight"], W[p + "attn.in_proj_bias"])
-        if save:
-            a, lse = O.attn_fwd(qkv, B, S, H, causal, want_lse=True, cu=cu)
-        else:
-            a, lse = O.attn_fwd(qkv, B, S, H, causal, cu=cu), None
-        x2 = O.linear_fwd(a, W[p + "attn.out_proj.weight"], W[p + "attn.out_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x,
-                          out_dtype=f32)
-        if save:
-            h2, mean2, rstd2 = O.layernorm_fwd(x2, W[p + "ln_2.weight"], W[p + "ln_2.bias"], want_stats=True)
-            f = torch.empty((x.shape[0], 4 * x.shape[1]), device=x.device, dtype=bf16)
-        else:
-            h2 = O.layernorm_fwd(x2, W[p + "ln_2.weight"], W[p + "ln_2.bias"])
-            f = None
-        g = O.linear_fwd(h2, W[p + "mlp.c_fc.weight"], W[p + "mlp.c_fc.bias"], epilogue=L.EPI_QUICKGELU, preact=f)
-        y = O.linear_fwd(g, W[p + "mlp.c_proj.weight"], W[p + "mlp.c_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x2,
-                         out_dtype=f32)
-        if save:
-            saved.blocks.append(BlockSaved(x, mean1, rstd1, h1, qkv, a, lse, x2, mean2, rstd2, h2, f, g))
+            y, blk = _block_fwd(W, p, x, B, S, H, causal, saved is not None, cu)
+            if saved is not None:
+                saved.blocks.append(blk)
         x = y
     return x
 
@@ -142,25 +157,46 @@ def _last_block_fwd(W, p, x, B, S, H, causal, saved, pool_rows, cu=None):
     return y
 
 
-def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved, on_layer_done=None, cu=None):
+def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved, on_layer_done=None, cu=None,
+               wgrad_stream=None):
     """Bias gradients are column sums of the gradient stream; they are produced by the kernel that
     WRITES each tensor (GEMM epilogue ``colsum`` / LayerNorm-backward ``dx_colsum``) instead of by
     separate reduction passes -- only the Q third of dqkv (written by the attention backward) and the
-    incoming dy of the last block use the stand-alone colsum kernel."""
+    incoming dy of the last block use the stand-alone colsum kernel.
+
+    ``wgrad_stream``: the weight-gradient GEMMs (and the Q-bias column sum) have no consumer before the
+    optimiser, so they leave the critical path dgrad -> LayerNorm' -> dgrad -> attention' -> dgrad: they are
+    issued on this second stream, each behind the kernel that produced its operand, and fill the SMs the
+    critical path leaves idle (ramps, tails, partial waves -- at 128 pairs / GPU that is half the machine).
+    A layer's activations are released one layer late, after an event says its weight gradients are done."""
+    cur = torch.cuda.current_stream(dy.device) if wgrad_stream is not None else None
+    held, held_ev = None, None
+
+    def wgrad(dy_, x_, out_):
+        if wgrad_stream is None:
+            return O.linear_wgrad(dy_, x_, out_)
+        wgrad_stream.wait_stream(cur)          # dy_ has just been produced on the tower's stream
+        with torch.cuda.stream(wgrad_stream):
+            O.linear_wgrad(dy_, x_, out_)
+
     O.colsum(dy, G[_blk(prefix, layers - 1) + "mlp.c_proj.bias"])
     for i in reversed(range(layers)):
         p = _blk(prefix, i)
         s: BlockSaved = saved.blocks[i]
+        if s.qkv is None:   # activation recompute: only the block's input was kept
+            _, s = _block_fwd(W, p, s.x, B, S, H, causal, True, cu)
+        dy_in = dy
         # ---- MLP branch: y = x2 + c_proj(gelu(c_fc(ln_2(x2))))
-        O.linear_wgrad(dy, s.g, G[p + "mlp.c_proj.weight"])
+        wgrad(dy, s.g, G[p + "mlp.c_proj.weight"])
         df = O.linear_dgrad(dy, W[p + "mlp.c_proj.weight"], epilogue=L.EPI_QUICKGELU_BWD, aux=s.f,
                             colsum=G[p + "mlp.c_fc.bias"])
-        O.linear_wgrad(df, s.h2, G[p + "mlp.c_fc.weight"])
+        wgrad(df, s.h2, G[p + "mlp.c_fc.weight"])
         dh2 = O.linear_dgrad(df, W[p + "mlp.c_fc.weight"])
         dx2 = O.layernorm_bwd(dh2, s.x2, W[p + "ln_2.weight"], s.mean2, s.rstd2, G[p + "ln_2.weight"],
                               G[p + "ln_2.bias"], dres=dy, dx_colsum=G[p + "attn.out_proj.bias"])
         # ---- attention branch: x2 = x + out_proj(attn(in_proj(ln_1(x))))
-        O.linear_wgrad(dx2, s.a if s.pool is None else s.a_p, G[p + "attn.out_proj.weight"])
+        wgrad(dx2, s.a if s.pool is None else s.a_p, G[p + "attn.out_proj.weight"])
+        dx2_in = dx2
         # in_proj_bias gradient = column sums of dqkv = [dQ | dK | dV] without reading all of dqkv again:
         #   V third: sum_kv dV = sum_q (P^T dO) = sum_q dO because softmax rows sum to one -> the column
         #            sums of `da`, produced by this dgrad GEMM's epilogue;
@@ -174,16 +210,31 @@ def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved, on_
             da = O.scatter_rows(da, s.pool, s.a.shape[0])
             dx2 = O.scatter_rows(dx2, s.pool, s.a.shape[0])
         dqkv = O.attn_bwd(s.qkv, s.a, s.lse, da, B, S, H, causal, cu=cu)
-        O.colsum(dqkv[:, :d_model], gb[:d_model])
-        O.linear_wgrad(dqkv, s.h1, G[p + "attn.in_proj_weight"])
+        if wgrad_stream is None:
+            O.colsum(dqkv[:, :d_model], gb[:d_model])
+        wgrad(dqkv, s.h1, G[p + "attn.in_proj_weight"])
+        if wgrad_stream is not None:
+            with torch.cuda.stream(wgrad_stream):
+                O.colsum(dqkv[:, :d_model], gb[:d_model])
         dh1 = O.linear_dgrad(dqkv, W[p + "attn.in_proj_weight"])
         # dx of this LayerNorm is the dy of block i-1: its column sums are that block's c_proj bias gradient
         prev_bias = G[_blk(prefix, i - 1) + "mlp.c_proj.bias"] if i > 0 else None
         dy = O.layernorm_bwd(dh1, s.x, W[p + "ln_1.weight"], s.mean1, s.rstd1, G[p + "ln_1.weight"],
                              G[p + "ln_1.bias"], dres=dx2, dx_colsum=prev_bias)
-        saved.blocks[i] = None  # release this layer's activations
-        if on_layer_done is not None:  # every parameter gradient of layers >= i is final now
+        saved.blocks[i] = None  # release this layer's activations ...
+        if wgrad_stream is not None:
+            # ... one layer late: the PREVIOUS layer's weight gradients must have read them first
+            if held_ev is not None:
+                cur.wait_event(held_ev)
+            held = (s, dy_in, df, dx2_in, dqkv)   # noqa: F841 -- keeps the operands of this layer's wgrads alive
+            held_ev = torch.cuda.Event()
+            held_ev.record(wgrad_stream)
+        del s
+        if on_layer_done is not None:  # every parameter gradient of layers >= i is final now (given wgrad_stream's work)
             on_layer_done(i)
+    if wgrad_stream is not None:
+        cur.wait_stream(wgrad_stream)
+        del held
     return dy
 
 
@@ -233,7 +284,7 @@ def _vision_index(B, n, device):
 
 
 # clip.model.VisionTransformer.forward
-def vision_fwd(W, cfg, image, save: bool):
+def vision_fwd(W, cfg, image, save: bool, recompute: bool = False):
     B = image.shape[0]
     p, n, d = cfg.vision_patch_size, cfg.vision_tokens, cfg.vision_width
     H = d // 64
@@ -249,7 +300,7 @@ def vision_fwd(W, cfg, image, save: bool):
                         neg_row=W["class_embedding"], add=W["positional_embedding"], add_period=n, pre_out=pre,
                         want_stats=save, out_dtype=f32)  # the residual stream is fp32
     x, mean0, rstd0 = r if save else (r, None, None)
-    saved = TowerSaved() if save else None
+    saved = TowerSaved(recompute=recompute) if save else None
     x = blocks_fwd(W, "transformer.", cfg.vision_layers, x, B, n, H, False, saved,
                    cls_rows if POOL_LAST_BLOCK else None)
     if POOL_LAST_BLOCK:
@@ -260,14 +311,15 @@ def vision_fwd(W, cfg, image, save: bool):
     return feat, saved
 
 
-def vision_bwd(W, G, cfg, saved: TowerSaved, dfeat, on_layer_done=None):
+def vision_bwd(W, G, cfg, saved: TowerSaved, dfeat, on_layer_done=None, wgrad_stream=None):
     e = saved.extra
     B, n, d = e["B"], cfg.vision_tokens, cfg.vision_width
     H = d // 64
     pooled, mean, rstd = e["head"]
     dx = _pool_project_bwd(W, G, dfeat, e["x_last"], e["cls_rows"], "ln_post.weight", "ln_post.bias", "proj", pooled,
                            mean, rstd)
-    dx = blocks_bwd(W, G, "transformer.", cfg.vision_layers, dx, B, n, H, False, saved, on_layer_done)
+    dx = blocks_bwd(W, G, "transformer.", cfg.vision_layers, dx, B, n, H, False, saved, on_layer_done,
+                    wgrad_stream=wgrad_stream)
     dpre = O.layernorm_bwd(dx, e["pre"], W["ln_pre.weight"], e["mean0"], e["rstd0"], G["ln_pre.weight"],
                            G["ln_pre.bias"])
     dpatch = O.vision_assemble_bwd(dpre, B, n, G["positional_embedding"], G["class_embedding"])
@@ -276,14 +328,14 @@ def vision_bwd(W, G, cfg, saved: TowerSaved, dfeat, on_layer_done=None):
 
 # ------------------------------------------------------------------------------------------------
 # clip.model.CLIP.encode_text
-def text_fwd(W, cfg, text, save: bool, rows=None):
+def text_fwd(W, cfg, text, save: bool, rows=None, recompute: bool = False):
     """``rows``: static row count of the packed layout (>= sum of EOT position + 1; see PACK_TEXT); None lets
     this function decide -- unpacked for small batches, else packed to the exact count (one host sync)."""
     B, S = text.shape
     d = cfg.transformer_width
     H = cfg.transformer_heads
     ids = text.to(i32).contiguous()
-    saved = TowerSaved() if save else None
+    saved = TowerSaved(recompute=recompute) if save else None
     cu = None
     if PACK_TEXT and S <= 128 and (rows is not None or B * S >= PACK_MIN_ROWS):
         # keep positions 0 .. EOT of every caption only
@@ -303,14 +355,15 @@ def text_fwd(W, cfg, text, save: bool, rows=None):
     return feat, saved
 
 
-def text_bwd(W, G, cfg, saved: TowerSaved, dfeat, on_layer_done=None):
+def text_bwd(W, G, cfg, saved: TowerSaved, dfeat, on_layer_done=None, wgrad_stream=None):
     e = saved.extra
     B, S = e["B"], e["S"]
     H = cfg.transformer_heads
     pooled, mean, rstd = e["head"]
     dx = _pool_project_bwd(W, G, dfeat, e["x_last"], e["eot"], "ln_final.weight", "ln_final.bias", "text_projection",
                            pooled, mean, rstd)
-    dx = blocks_bwd(W, G, "transformer.", cfg.transformer_layers, dx, B, S, H, True, saved, on_layer_done, e.get("cu"))
+    dx = blocks_bwd(W, G, "transformer.", cfg.transformer_layers, dx, B, S, H, True, saved, on_layer_done, e.get("cu"),
+                    wgrad_stream=wgrad_stream)
     if e.get("cu") is not None:  # packed rows; the dropped positions have zero gradient
         O.embed_tokens_packed_bwd(e["ids"], dx, e["cu"], G["token_embedding.weight"], G["positional_embedding"])
     else:

@@ -172,7 +172,7 @@ class ClipTrainer:
     ``get_linear_schedule_with_warmup(5000, total)`` (CLIP/train.py:143-147)."""
 
     def __init__(self, model, lr=1e-5, betas=(0.9, 0.999), eps=1e-6, weight_decay=0.0, warmup_steps=5000,
-                 total_steps=None, group=None, device=None, shard_optimizer=True):
+                 total_steps=None, group=None, device=None, shard_optimizer=True, recompute=False):
         self.model = model
         self.cfg = model.cfg
         self.group = group
@@ -181,6 +181,7 @@ class ClipTrainer:
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.warmup_steps, self.total_steps = warmup_steps, total_steps
         self.step_count = 0
+        self.recompute = bool(recompute)   # activation recompute per block (towers.blocks_fwd): 1/9 of the activation memory
         self.stores = {k: model._store(k, self.device) for k in ("visual", "text")}
         # ZeRO-1 style optimiser sharding for N > 1: gradients are REDUCE-SCATTERED (each rank receives
         # the sum of its 1/N slice), AdamW runs on that slice only (fp32 master / moments are 1/N the
@@ -224,6 +225,10 @@ class ClipTrainer:
         self.last_correct = None
         self.two_streams = True
         self._tower_streams = None
+        # weight-gradient GEMMs on a second stream per tower (towers.blocks_bwd); B200CLIP_WGRAD_STREAM=0 disables
+        import os
+        self.wgrad_streams = os.environ.get("B200CLIP_WGRAD_STREAM", "1") != "0"
+        self._wgrad_streams = None
         self._hyper_live = False  # True while a CUDA-graph capture / warm-up wants device-side lr
         # CUDA-graph mode (enable_cuda_graph): step-dependent scalars live in device memory
         self._use_graph = False
@@ -313,11 +318,11 @@ class ClipTrainer:
         else:
             sv = stt = main
         with torch.cuda.stream(sv):
-            img_f, saved_i = T.vision_fwd(Wv, cfg, image, True)
+            img_f, saved_i = T.vision_fwd(Wv, cfg, image, True, recompute=self.recompute)
         if text_rows == "auto":
             text_rows = self.text_rows(text)
         with torch.cuda.stream(stt):
-            txt_f, saved_t = T.text_fwd(Wt, cfg, text, True, rows=text_rows)
+            txt_f, saved_t = T.text_fwd(Wt, cfg, text, True, rows=text_rows, recompute=self.recompute)
         if two:
             main.wait_stream(sv)
             main.wait_stream(stt)
@@ -333,10 +338,18 @@ class ClipTrainer:
         work = []
         hyper = self._hyper if self._hyper_live else None
         fused = fused_update and self.sharded
-        for k, s_tower, bwd, W_, saved_, dfeat in (("visual", sv, T.vision_bwd, Wv, saved_i, d_img),
-                                                   ("text", stt, T.text_bwd, Wt, saved_t, d_txt)):
+        wg = (None, None)
+        if self.wgrad_streams and two:
+            if self._wgrad_streams is None:
+                self._wgrad_streams = (torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev))
+            wg = self._wgrad_streams
+        for k, s_tower, bwd, W_, saved_, dfeat, s_wg in (("visual", sv, T.vision_bwd, Wv, saved_i, d_img, wg[0]),
+                                                         ("text", stt, T.text_bwd, Wt, saved_t, d_txt, wg[1])):
             with torch.cuda.stream(s_tower):
-                bwd(W_, self.G[k], cfg, saved_, dfeat, self._chunk_callback(k, s_tower, hyper) if fused else None)
+                if s_wg is not None:
+                    s_wg.wait_stream(s_tower)
+                bwd(W_, self.G[k], cfg, saved_, dfeat, self._chunk_callback(k, s_tower, hyper, s_wg) if fused else None,
+                    wgrad_stream=s_wg)
                 if self.world > 1:
                     if fused:
                         self._sharded_update(k, hyper, ready=-1)  # what only becomes final at the end
@@ -379,7 +392,7 @@ class ClipTrainer:
                     self.v[k][moff:moff + n], **self._adam_args(hyper))
             dist.all_gather_into_tensor(st.w[a:b], st.w[lo:lo + n], group=grp)
 
-    def _chunk_callback(self, k, tower_stream, hyper):
+    def _chunk_callback(self, k, tower_stream, hyper, wgrad_stream=None):
         """Called by the tower's backward after each transformer block: chunks that just became final
         are reduced / updated / re-gathered on a side stream while the backward goes on."""
         table = self.chunk_ready[k]
@@ -393,6 +406,8 @@ class ClipTrainer:
             idx = table.get(layer)
             if idx:
                 side.wait_stream(tower_stream)
+                if wgrad_stream is not None:   # the weight gradients of the finished layers come from this stream
+                    side.wait_stream(wgrad_stream)
                 with torch.cuda.stream(side):
                     self._sharded_update(k, hyper, only=idx)
         return done

@@ -631,3 +631,23 @@ def test_trainer_keeps_state_dict_fresh():
     full = tr.master["visual"]
     name0, p0, o0, s0 = tr.stores["visual"].entries[0]
     assert torch.equal(after["visual." + name0].reshape(-1), full[o0:o0 + p0.numel()])
+
+
+def test_activation_recompute_is_exact():
+    """ClipTrainer(recompute=True) keeps only each block's input and re-runs the block forward inside the backward
+    (BASELINE config 5 needs it to fit); loss and every gradient must equal the stored-activation path."""
+    from construction_clip_b200.train import ClipTrainer
+    name, B = "ViT-B/32", 9
+    orc = oracle_model(name)
+    img, tok = _inputs(name, B, B, 30)
+    out = []
+    for rc in (False, True):
+        m = device_model(name, orc).train()
+        tr = ClipTrainer(m, recompute=rc)
+        loss = tr.forward_backward(img.cuda(), tok.cuda())
+        out.append((loss.item(), {k: g.clone() for k, g in tr.grads.items()}))
+    (l0, g0), (l1, g1) = out
+    assert abs(l1 - l0) <= 1e-5 * abs(l0)
+    for k in g0:
+        assert cosine(g1[k].cpu(), g0[k].cpu()) > 0.9999, k
+        assert abs(g1[k].norm().item() / g0[k].norm().item() - 1) < 1e-2, k

@@ -8,7 +8,7 @@
 set -u
 PASS=${1:-launches}
 R=${2:-r01}
-CMD="python tools/profile_one_step.py"
+CMD="python tools/profile_one_step.py ${PAIRS:-1024}"
 $CMD > gpurun_out/${R}_plain.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/${R}_plain.log; exit 1; }
 tail -1 gpurun_out/${R}_plain.log
 case $PASS in

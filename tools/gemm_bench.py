@@ -7,6 +7,9 @@ from construction_clip_b200 import lib as L, ops as O
 bf16, f32 = torch.bfloat16, torch.float32
 dev = "cuda"
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+# text rows: the packed tower's bucketed row count for U{3..76} captions (mean 40.5 + EOT), or argv[2]
+_g = max(256, -(-(B * 77 // 32) // 256) * 256)
+TXT_ROWS = int(sys.argv[2]) if len(sys.argv) > 2 else -(-int(B * 41.5) // _g) * _g
 
 
 def timeit(fn, iters=10):
@@ -23,7 +26,7 @@ def timeit(fn, iters=10):
 
 
 rows = []
-for tower, M, d in (("vis", B * 50, 768), ("txt", B * 77, 512)):
+for tower, M, d in (("vis", B * 50, 768), ("txt", TXT_ROWS, 512)):
     x = torch.randn(M, d, device=dev).to(bf16)
     x4 = torch.randn(M, 4 * d, device=dev).to(bf16)
     x3 = torch.randn(M, 3 * d, device=dev).to(bf16)

@@ -11,12 +11,19 @@ for STAGE in "$@"; do
         tests)        timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 > gpurun_out/${TAG}_tests.log 2>&1 ;;
         tests_all)    timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/${TAG}_tests.log 2>&1 ;;
         bench)        timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
+        bench_nv)     B200CLIP_BENCH_VARIANTS=0 timeout 400 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
         bench_nopack) B200CLIP_PACK_TEXT=0 B200CLIP_BENCH_VARIANTS=0 timeout 400 python bench.py --steps 5 > gpurun_out/${TAG}_bench_nopack.json 2> gpurun_out/${TAG}_bench_nopack.err ;;
         bench128)     B200CLIP_BENCH_VARIANTS=0 BENCH_GLOBAL_BATCH=128 timeout 400 python bench.py --steps 20 > gpurun_out/${TAG}_bench128.json 2> gpurun_out/${TAG}_bench128.err ;;
         gemm)         timeout 300 python tools/gemm_bench.py 1024 > gpurun_out/${TAG}_gemm1024.txt 2>&1 ;;
         gemm128)      timeout 300 python tools/gemm_bench.py 128 > gpurun_out/${TAG}_gemm128.txt 2>&1 ;;
         micro)        timeout 300 python tools/ncu_micro.py --time > gpurun_out/${TAG}_micro.txt 2>&1 ;;
         infer)        timeout 400 python tools/infer_bench.py > gpurun_out/${TAG}_infer.txt 2>&1 ;;
+        launches128)  PAIRS=128 bash tools/collect_profiles.sh launches ${TAG}_b128 > gpurun_out/${TAG}_launches128.log 2>&1 ;;
+        launches)     PAIRS=1024 bash tools/collect_profiles.sh launches ${TAG}_b1024 > gpurun_out/${TAG}_launches1024.log 2>&1 ;;
+        dist2)        timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29541 tools/dist_check.py > gpurun_out/${TAG}_dist2.log 2>&1 ;;
+        bench2)       B200CLIP_BENCH_VARIANTS=0 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/${TAG}_bench2.json 2> gpurun_out/${TAG}_bench2.err ;;
+        graph128)     timeout 400 python tools/graph_bench.py 128 > gpurun_out/${TAG}_graph128.txt 2>&1 ;;
+        graph1024)    timeout 400 python tools/graph_bench.py 1024 > gpurun_out/${TAG}_graph1024.txt 2>&1 ;;
         smoke)        timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1 ;;
         *)            echo "unknown stage $STAGE" ;;
     esac
