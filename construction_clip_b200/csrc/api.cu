@@ -38,6 +38,21 @@ int make_tmap_bf16_2d(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint
         set_error("tensor map: bad box %u x %u", box0, box1);
         return B200CLIP_ERR_ARG;
     }
+    // cache lookup (one context is driven by one host thread at a time; entries are written whole before use)
+    const uint64_t key[4] = {reinterpret_cast<uint64_t>(ptr), dim0, dim1,
+                             (pitch_elems << 20) | (static_cast<uint64_t>(box0) << 10) | box1};
+    TmapCacheEntry* slot = nullptr;
+    if (ctx->tmap_cache != nullptr) {
+        uint64_t h = key[0] * 0x9E3779B97F4A7C15ull ^ key[1] * 0xC2B2AE3D27D4EB4Full ^ key[2] * 0x165667B19E3779F9ull ^ key[3];
+        h ^= h >> 29;
+        slot = &ctx->tmap_cache[h % kTmapCacheSize];
+        if (slot->key[0] == key[0] && slot->key[1] == key[1] && slot->key[2] == key[2] && slot->key[3] == key[3]) {
+            memcpy(out, &slot->map, sizeof(CUtensorMap));
+            ++ctx->tmap_hits;
+            return B200CLIP_OK;
+        }
+        ++ctx->tmap_misses;
+    }
     cuuint64_t gdim[2] = {dim0, dim1};
     cuuint64_t gstride[1] = {pitch_elems * 2};
     cuuint32_t box[2] = {box0, box1};
@@ -49,6 +64,10 @@ int make_tmap_bf16_2d(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint
         set_error("cuTensorMapEncodeTiled failed (%d): dims %llu x %llu pitch %llu box %u x %u", (int)r,
                   (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)pitch_elems, box0, box1);
         return B200CLIP_ERR_CUDA;
+    }
+    if (slot != nullptr) {
+        memcpy(&slot->map, out, sizeof(CUtensorMap));
+        memcpy(slot->key, key, sizeof(key));
     }
     return B200CLIP_OK;
 }
@@ -93,6 +112,8 @@ int b200clip_ctx_create(b200clip_ctx** out, int device) {
     B200_CHECK_CUDA(cudaSetDevice(device));
     B200_CHECK_CUDA(cudaFree(0));  // make sure the primary context exists
     b200clip_ctx* ctx = new b200clip_ctx();
+    ctx->tmap_cache = nullptr;
+    ctx->tmap_hits = ctx->tmap_misses = 0;
     ctx->device = device;
     ctx->num_sms = prop.multiProcessorCount;
     void* fn = nullptr;
@@ -104,9 +125,12 @@ int b200clip_ctx_create(b200clip_ctx** out, int device) {
         return B200CLIP_ERR_CUDA;
     }
     ctx->encode_tiled = reinterpret_cast<PFN_encodeTiled>(fn);
+    ctx->tmap_cache = (getenv("B200CLIP_TMAP_CACHE") && atoi(getenv("B200CLIP_TMAP_CACHE")) == 0)
+                          ? nullptr : new TmapCacheEntry[kTmapCacheSize]();
     int rc = b200::init_gemm(ctx);
     if (rc == 0) rc = b200::init_attention(ctx);
     if (rc != 0) {
+        delete[] ctx->tmap_cache;
         delete ctx;
         return rc;
     }
@@ -115,6 +139,7 @@ int b200clip_ctx_create(b200clip_ctx** out, int device) {
 }
 
 int b200clip_ctx_destroy(b200clip_ctx* ctx) {
+    if (ctx != nullptr) delete[] ctx->tmap_cache;
     delete ctx;
     return B200CLIP_OK;
 }

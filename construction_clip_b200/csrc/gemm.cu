@@ -53,13 +53,22 @@ constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kStageBytesA = BM * BK * 2;  // 16 KB
 constexpr int kEpiStageBytes = 32 * 128;   // per-warp staging: 32 rows x 128 B, XOR-swizzled
 
+// Tile widths BN in {96, 128, 160, 192, 224, 256}: with M / 128 row tiles fixed by the batch, the width is what
+// lets the launcher fit the tile count to the 148 SMs (e.g. 6400 x 768: 150 tiles of 256 = 2 waves, 250 tiles
+// of 160 = 1.7 waves of 0.7-cost tiles).  Shared-memory stages are sized for BN rounded up to 64: an MN-major
+// B operand arrives in 64-column swizzle atoms (the last atom of a 96 / 160 / 224 tile is loaded whole and
+// read half).
 template <int BN>
 struct GemmCfg {
-    static constexpr int kStageBytesB = BN * BK * 2;
+    static_assert(BN % 32 == 0 && BN >= 64 && BN <= 256, "tile width");
+    static constexpr int kBNSmem = (BN + 63) / 64 * 64;
+    static constexpr int kStageBytesB = kBNSmem * BK * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-    static constexpr int kStages = (BN >= 192) ? 4 : 6;
-    static constexpr int kTmemCols = (BN > 128) ? 512 : 256;  // two accumulator stages (power of two)
+    static constexpr int kStages = (kBNSmem >= 192) ? 4 : 6;
+    static constexpr int kTmemCols = (2 * BN > 256) ? 512 : 256;  // two accumulator stages (power of two)
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024;  // + align slack
+    static constexpr int kBlocks = BN / 32;           // 32-column epilogue blocks per tile
+    static constexpr int kBlocks0 = (kBlocks + 1) / 2;  // column half 0 (warps 2-5) drains these, half 1 the rest
 };
 
 struct GemmParams {
@@ -402,18 +411,21 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
     // mainloop's operand loads: up to 2.4x slower).
     constexpr bool kHasAux = (EPI == B200CLIP_EPI_QUICKGELU_BWD);
     constexpr int kAuxElem = (EPI == B200CLIP_EPI_RESIDUAL && OUT_F32) ? 4 : 2;
+    constexpr int kBlocks0 = (BN / 32 + 1) / 2;                     // blocks of column half 0
+    const int blk0 = half ? kBlocks0 : 0;                           // first block of this warp's half
+    const int nblk_half = half ? BN / 32 - kBlocks0 : kBlocks0;     // blocks this warp drains per tile
     auto prefetch_aux = [&](int wq) {
         if constexpr (kHasAux && B200_EPI_AUX_PREFETCH) {
             if (wq < num_work) {
                 const int tq = wq / p.split_k;
                 const int row = (tq / p.num_n_tiles) * (PAIR ? 2 * BM : BM) + rank * BM + quad * 32 + lane;
-                const int nb = (tq % p.num_n_tiles) * BN + half * (BN / 2);
-                const int ncol = min(BN / 2, p.N - nb);  // N % 8 == 0: a multiple of 16 bytes either way
+                const int nb = (tq % p.num_n_tiles) * BN + blk0 * 32;
+                const int ncol = min(nblk_half * 32, p.N - nb);  // N % 8 == 0: a multiple of 16 bytes either way
                 if (row < p.M && ncol > 0) {
                     const uint8_t* a = reinterpret_cast<const uint8_t*>(p.aux) +
                                        (static_cast<int64_t>(row) * p.ldaux + nb) * kAuxElem;
 #pragma unroll
-                    for (int l = 0; l < (BN / 2) * kAuxElem / 128; ++l)
+                    for (int l = 0; l < kBlocks0 * 32 * kAuxElem / 128; ++l)
                         if (l * 128 < ncol * kAuxElem) prefetch_l2_line(a + l * 128);
                 }
             }
@@ -424,12 +436,12 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
         prefetch_aux(w + wstep);
         const int tile = w / p.split_k;
         const int m_base = (tile / p.num_n_tiles) * (PAIR ? 2 * BM : BM) + rank * BM + quad * 32;
-        const int n_base = (tile % p.num_n_tiles) * BN + half * (BN / 2);
-        int nblk = (BN / 2) >> 5;
+        const int n_base = (tile % p.num_n_tiles) * BN + blk0 * 32;
+        int nblk = nblk_half;
         const int valid = (p.N - n_base + 31) >> 5;  // blocks with at least one real column (warp-uniform)
-        if (valid < nblk) nblk = valid;
+        if (valid < nblk) nblk = valid < 0 ? 0 : valid;
         const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) +
-                               static_cast<uint32_t>(as * BN + half * (BN / 2));
+                               static_cast<uint32_t>(as * BN + blk0 * 32);
         const bool full = B200_EPI_FULL_SPEC && (m_base + 32 <= p.M) && (n_base + nblk * 32 <= p.N);
 #define B200_DRAIN(FULL, PRE)                                                                                      \
     drain_tile<EPI, OUT_F32, ATOMIC, FULL, PRE, PAIR>(p, &tmem_full_bar[as], aphase, &tmem_empty_bar[as], taddr, m_base, \
@@ -514,7 +526,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    // bytes the loads below deliver: a K-major B box is exactly BN rows, MN-major B comes in 64-column atoms
+                    mbar_arrive_expect_tx(&full_bar[stage], kStageBytesA + (B_MN ? Cfg::kBNSmem : BN) * BK * 2);
                     uint8_t* sA = smem + stage * Cfg::kStageBytes;
                     uint8_t* sB = sA + kStageBytesA;
                     if constexpr (!A_MN) {
@@ -528,7 +541,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         tma_load_2d(sB, &tmB, &full_bar[stage], kb * BK, n0);
                     } else {
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
+                        for (int j = 0; j < Cfg::kBNSmem / 64; ++j)
                             tma_load_2d(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
                     }
                     if (++stage == kStages) {
@@ -839,6 +852,12 @@ int init_gemm(b200clip_ctx*) {
     if ((rc = set_attr<128, false, false>())) return rc;
     if ((rc = set_attr<128, false, true>())) return rc;
     if ((rc = set_attr<128, true, true>())) return rc;
+    if ((rc = set_attr<224, false, false>())) return rc;
+    if ((rc = set_attr<224, false, true>())) return rc;
+    if ((rc = set_attr<160, false, false>())) return rc;
+    if ((rc = set_attr<160, false, true>())) return rc;
+    if ((rc = set_attr<96, false, false>())) return rc;
+    if ((rc = set_attr<96, false, true>())) return rc;
     if ((rc = set_attr_pair<false, false>())) return rc;
     if ((rc = set_attr_pair<false, true>())) return rc;
     if ((rc = set_attr_pair<true, true>())) return rc;
@@ -953,38 +972,46 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
         return !(e && atoi(e) == 0);
     }();
     const int clusters = ctx->num_sms / 2;
+    const int sms = ctx->num_sms;
+    const int64_t m_tiles = ceil_div(M, BM);
     const int64_t tiles_pair = ceil_div(M, 2 * BM) * ceil_div(N, 256);
-    bool use_pair = pair_enabled && N >= 256 && M >= 2 * BM && (tiles_pair >= clusters || (out_f32 && epilogue == B200CLIP_EPI_NONE));
-    // tile width: 256 when that still fills the machine, else 128 for more CTAs
-    const int64_t tiles256 = ceil_div(M, BM) * ceil_div(N, 256);
-    bool use256 = (N >= 256) && (tiles256 >= ctx->num_sms || (out_f32 && epilogue == B200CLIP_EPI_NONE));
-    bool use192 = false;
-    const char* force_bn = getenv("B200CLIP_FORCE_BN");  // tuning / experiments only
+    const bool pair_ok = pair_enabled && N >= 256 && M >= 2 * BM;
+    const bool amn = a_major == B200CLIP_MAJOR_MN, bmn = b_major == B200CLIP_MAJOR_MN;
+    auto tiles_of = [&](int bn) { return m_tiles * ceil_div(N, bn); };
+    // Tile shape.  Atomic (split-K / accumulating) fp32 outputs -- the weight gradients -- take the widest
+    // tile that exists for them and balance the machine through split-K instead.  Everything else has ONE
+    // work item per tile, so the shape with the smallest makespan  waves x tile-time  wins: small per-GPU
+    // batches (8-GPU strong scaling) leave the 256 x 256 pair tiles with a nearly empty last wave (75 tiles
+    // on 74 clusters = 2 waves), and with the row count fixed by the batch the tile WIDTH is the free
+    // parameter.  Tile time relative to a 128 x 256 tile on one SM: 0.24 + 0.76 * BN / 256 (measured 1.00 /
+    // 0.80 / 0.62 at 256 / 192 / 128 on the ViT-B/32 layer shapes); the pair kernel's 256 x 256 tile on two
+    // SMs costs 0.95.  B200CLIP_FORCE_BN=<width> pins the single-CTA width (tuning / experiments only).
+    bool use_pair = false;
+    int bn = 256;
+    const char* force_bn = getenv("B200CLIP_FORCE_BN");
+    const bool atomic_like = out_f32 && (split_k != 1 || accumulate);
     if (force_bn) {
-        if (atoi(force_bn) == 128) use256 = false;
-        if (atoi(force_bn) == 256 && N >= 256) use256 = true;
-        if (atoi(force_bn) == 192 && N >= 192) use192 = true, use256 = false;
-    } else if (!(out_f32 && (split_k != 1 || accumulate))) {
-        // One work item per tile (no split-K): pick the tile shape with the smallest makespan
-        // waves x tile-time.  Small per-GPU batches (strong scaling) leave the 256 x 256 pair tiles
-        // with a nearly empty last wave (75 tiles on 74 clusters = 2 waves); 128 x 192 tiles then win.
-        // Tile times relative to a 128 x 256 tile on one SM, measured on the ViT-B/32 layer shapes.
-        const int sms = ctx->num_sms;
-        const double c_pair = (pair_enabled && N >= 256 && M >= 2 * BM)
-                                  ? 0.95 * static_cast<double>(ceil_div(tiles_pair, clusters)) : 1e30;
-        const double c_256 = N >= 256 ? 1.00 * static_cast<double>(ceil_div(tiles256, sms)) : 1e30;
-        const double c_192 = N >= 192 ? 0.80 * static_cast<double>(ceil_div(ceil_div(M, BM) * ceil_div(N, 192), sms)) : 1e30;
-        const double c_128 = 0.62 * static_cast<double>(ceil_div(ceil_div(M, BM) * ceil_div(N, 128), sms));
-        double best = c_pair;
-        use_pair = c_pair < 1e29;
-        use256 = use192 = false;
-        if (c_256 < best - 1e-9) best = c_256, use_pair = false, use256 = true, use192 = false;
-        if (c_192 < best - 1e-9) best = c_192, use_pair = false, use256 = false, use192 = true;
-        if (c_128 < best - 1e-9) best = c_128, use_pair = false, use256 = false, use192 = false;
+        bn = atoi(force_bn);
+        if (bn != 96 && bn != 128 && bn != 160 && bn != 192 && bn != 224 && bn != 256) bn = 256;
+        if (amn && (bn % 64)) bn = 256;
+        while (bn > 96 && bn > N + 31) bn -= 32;
+    } else if (atomic_like) {
+        use_pair = pair_ok;
+        bn = N >= 256 ? 256 : (N >= 192 ? 192 : 128);
+    } else {
+        double best = pair_ok ? 0.95 * static_cast<double>(ceil_div(tiles_pair, clusters)) : 1e30;
+        use_pair = pair_ok;
+        // (224 and 96 exist and are tested, but lost on every shape they were predicted to win at 128 pairs / GPU:
+        // fc fwd 33.9 -> 37.0 us, proj dgrad 38.8 -> 41.1 us with 224; 160 gains ~4 % on the N = 768 shapes)
+        static const int widths[] = {256, 192, 160, 128};
+        for (int w : widths) {
+            if (w > N + 31 && w != 96) continue;          // wider than the problem: the next width covers it
+            if (amn && (w % 64)) continue;                // (A MN-major, i.e. weight gradients: 64-multiples only)
+            const double c = (0.24 + 0.76 * w / 256.0) * static_cast<double>(ceil_div(tiles_of(w), sms));
+            if (c < best - 1e-9) best = c, use_pair = false, bn = w;
+        }
     }
-    const int64_t tiles = use_pair ? tiles_pair
-                          : use192 ? ceil_div(M, BM) * ceil_div(N, 192)
-                                   : (use256 ? tiles256 : ceil_div(M, BM) * ceil_div(N, 128));
+    const int64_t tiles = use_pair ? tiles_pair : tiles_of(bn);
     if (split_k <= 0) split_k = out_f32 ? choose_split_k(tiles, p.kb_total, use_pair ? clusters : ctx->num_sms) : 1;
     if (split_k > p.kb_total) split_k = p.kb_total;
     p.kb_per_split = static_cast<int>(ceil_div(p.kb_total, split_k));
@@ -993,24 +1020,28 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
     p.atomic_out = (out_f32 && (split_k > 1 || accumulate)) ? 1 : 0;
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool amn = a_major == B200CLIP_MAJOR_MN, bmn = b_major == B200CLIP_MAJOR_MN;
     if (use_pair) {
         if (!amn && !bmn) return launch_pair<false, false>(ctx, A, lda, B, ldb, p, st);
         if (!amn && bmn) return launch_pair<false, true>(ctx, A, lda, B, ldb, p, st);
         return launch_pair<true, true>(ctx, A, lda, B, ldb, p, st);
     }
-    if (use192) {
-        if (!amn && !bmn) return launch<192, false, false>(ctx, A, lda, B, ldb, p, st);
-        if (!amn && bmn) return launch<192, false, true>(ctx, A, lda, B, ldb, p, st);
-        return launch<192, true, true>(ctx, A, lda, B, ldb, p, st);
+#define B200_LAUNCH_BN(W)                                                                      \
+    case W:                                                                                    \
+        if (!amn && !bmn) return launch<W, false, false>(ctx, A, lda, B, ldb, p, st);          \
+        if (!amn && bmn) return launch<W, false, true>(ctx, A, lda, B, ldb, p, st);            \
+        break;
+    switch (bn) {
+        B200_LAUNCH_BN(96)
+        B200_LAUNCH_BN(160)
+        B200_LAUNCH_BN(224)
+        B200_LAUNCH_BN(128)
+        B200_LAUNCH_BN(192)
+        B200_LAUNCH_BN(256)
+        default: break;
     }
-    if (use256) {
-        if (!amn && !bmn) return launch<256, false, false>(ctx, A, lda, B, ldb, p, st);
-        if (!amn && bmn) return launch<256, false, true>(ctx, A, lda, B, ldb, p, st);
-        return launch<256, true, true>(ctx, A, lda, B, ldb, p, st);
-    } else {
-        if (!amn && !bmn) return launch<128, false, false>(ctx, A, lda, B, ldb, p, st);
-        if (!amn && bmn) return launch<128, false, true>(ctx, A, lda, B, ldb, p, st);
-        return launch<128, true, true>(ctx, A, lda, B, ldb, p, st);
-    }
+#undef B200_LAUNCH_BN
+    // A MN-major (weight gradients): 64-multiple widths only
+    if (bn >= 256) return launch<256, true, true>(ctx, A, lda, B, ldb, p, st);
+    if (bn >= 192) return launch<192, true, true>(ctx, A, lda, B, ldb, p, st);
+    return launch<128, true, true>(ctx, A, lda, B, ldb, p, st);
 }

@@ -14,10 +14,21 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+// Tensor-map cache: a training / inference loop encodes the same few hundred (pointer, extents, pitch,
+// box) descriptors every step -- weights never move, activations come back from the caching allocator at the same
+// addresses -- so the driver's encoder (~1 us each, 2-4 per launch) is consulted only on a miss.  Direct mapped.
+struct TmapCacheEntry {
+    uint64_t key[4];   // ptr, dim0, dim1, pitch << 20 | box0 << 10 | box1   (all zero = empty)
+    CUtensorMap map;
+};
+constexpr int kTmapCacheSize = 2048;
+
 struct b200clip_ctx {
     int device;
     int num_sms;
     PFN_encodeTiled encode_tiled;
+    TmapCacheEntry* tmap_cache;   // kTmapCacheSize entries, owned
+    uint64_t tmap_hits, tmap_misses;
 };
 
 namespace b200 {

@@ -323,6 +323,7 @@ class CLIP(nn.Module):
         self.logit_scale = nn.Parameter(torch.ones([]) * math.log(1 / 0.07))
         self._stores = {}
         self._trainer = None          # weakref to the ClipTrainer that owns the master weights, if any
+        self._igraphs = {}            # captured no-grad forwards, one per input shape (see _graphed)
         self.fp32_check_mode = False  # see set_fp32_check_mode
         self.initialize_parameters()
 
@@ -377,6 +378,7 @@ class CLIP(nn.Module):
     def _apply(self, fn, *a, **k):  # .to() / .float() / .half() invalidate the zero-copy links
         out = super()._apply(fn, *a, **k)
         self._stores = {}
+        self._igraphs = {}
         return out
 
     # ---------------------------------------------------------------------------------- forward
@@ -399,18 +401,75 @@ class CLIP(nn.Module):
             return fwd(store.W, self.cfg, inp)
         return _TowerFn.apply(self, which, need_grad, inp, *params)
 
+    # ------------------------------------------------------------------- launch-bound inference
+    # The reference's inference calls are tiny (CLIP/predict.py:40-54: a few images x 2..16 prompts;
+    # parse_coco.py:37-53: ONE image and three tower passes per iteration): ~180 kernel launches whose host
+    # cost (Python + ctypes + tensor-map encoding, ~15 us each) is 5-10x their GPU time.  Under torch.no_grad()
+    # such calls are captured ONCE per input shape into a CUDA graph and replayed: inputs are copied into the
+    # graph's static buffers, outputs are handed back as copies.  Large batches (where the host is not the
+    # limiter and the graph's private activation pool would be big) keep running eagerly.
+    GRAPH_MAX_ROWS = int(__import__("os").environ.get("B200CLIP_INFER_GRAPH_MAX_ROWS", "16384"))
+
+    def _graph_ok(self, *inputs):
+        if torch.is_grad_enabled() or self.fp32_check_mode or self.GRAPH_MAX_ROWS <= 0:
+            return False
+        if not all(t.is_cuda for t in inputs) or torch.cuda.is_current_stream_capturing():
+            return False
+        rows = 0
+        for t in inputs:
+            rows += t.shape[0] * (self.cfg.vision_tokens if t.dim() == 4 else t.shape[1])
+        return rows <= self.GRAPH_MAX_ROWS
+
+    def _graphed(self, tag, fn, *inputs):
+        key = (tag,) + tuple((tuple(t.shape), t.dtype, t.device) for t in inputs)
+        for which in ("visual", "text"):     # refresh the weight shadow OUTSIDE the graph (fp32 parameters that moved)
+            st = self._stores.get(which)
+            if st is not None:
+                st.sync()
+        ent = self._igraphs.get(key)
+        if ent is None:
+            static_in = [t.detach().clone() for t in inputs]
+            dev = inputs[0].device
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):        # warm-up: allocator, lazy stores, per-shape index caches
+                fn(*static_in)
+                fn(*static_in)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = fn(*static_in)
+            if len(self._igraphs) >= 8:          # a handful of shapes per process; drop the oldest
+                self._igraphs.pop(next(iter(self._igraphs)))
+            ent = self._igraphs[key] = (graph, static_in, out)
+        graph, static_in, out = ent
+        for s_, t in zip(static_in, inputs):
+            s_.copy_(t, non_blocking=True)
+        graph.replay()
+        return tuple(o.clone() for o in out) if isinstance(out, tuple) else out.clone()
+
     def encode_image(self, image):
         """[B,3,R,R] -> un-normalised [B, embed_dim] in the model dtype (parse_coco.py:43)."""
+        if self._graph_ok(image):
+            return self._graphed("img", lambda im: self._features("visual", im).to(self.dtype), image)
         return self._features("visual", image).to(self.dtype)
 
     def encode_text(self, text):
+        if self._graph_ok(text):
+            return self._graphed("txt", lambda tx: self._features("text", tx).to(self.dtype), text)
         return self._features("text", text).to(self.dtype)
+
+    def _forward_eager(self, image, text):
+        img_f = self._features("visual", image)
+        txt_f = self._features("text", text)
+        return _LogitsFn.apply(img_f, txt_f, self.logit_scale)
 
     def forward(self, image, text):
         """-> (logits_per_image [Bi,Bt], logits_per_text [Bt,Bi]); fp32 logits (CLIP/train.py:161)."""
-        img_f = self._features("visual", image)
-        txt_f = self._features("text", text)
-        logits_per_image = _LogitsFn.apply(img_f, txt_f, self.logit_scale)
+        if self._graph_ok(image, text):
+            logits_per_image = self._graphed("fwd", self._forward_eager, image, text)
+        else:
+            logits_per_image = self._forward_eager(image, text)
         return logits_per_image, logits_per_image.t()
 
 

@@ -73,6 +73,43 @@ def test_gemm_tn_wgrad(ops, M, N, K):
     _close(out, 2 * ref, 2e-3 * math.sqrt(K), 1e-3, f"gemm TN accumulate {M}x{N}x{K}")
 
 
+@pytest.mark.parametrize("bn", [96, 128, 160, 192, 224, 256])
+def test_gemm_every_tile_width(ops, bn, monkeypatch):
+    """The single-CTA kernel at every tile width (B200CLIP_FORCE_BN pins it), forward (B K-major) and dgrad
+    (B MN-major: 64-column swizzle atoms, the last one half used at 96 / 160 / 224), with ragged M and an N that
+    is not a multiple of the width, bias + fp32 residual / QuickGELU' epilogues with the fused column sum."""
+    from construction_clip_b200 import lib as L
+    monkeypatch.setenv("B200CLIP_FORCE_BN", str(bn))
+    monkeypatch.setenv("B200CLIP_GEMM_PAIR", "0")
+    M, N, K = 1000, 808, 320
+    a, w = _rand((M, K), seed=21), _rand((N, K), 0.05, seed=22)
+    bias = _rand((N,), seed=23)
+    auxf = torch.randn(M, N, device="cuda")
+    base = a.float() @ w.float().t() + bias.float()
+    _close(ops.gemm(a, w, bias=bias), base, 3e-2, 1e-2, f"bias bn={bn}")
+    _close(ops.gemm(a, w, bias=bias, epilogue=L.EPI_RESIDUAL, aux=auxf, out_dtype=f32), base + auxf, 1e-3, 1e-3,
+           f"residual fp32 bn={bn}")
+    pre = torch.empty((M, N), device="cuda", dtype=bf16)
+    got = ops.gemm(a, w, bias=bias, epilogue=L.EPI_QUICKGELU, preact=pre)
+    _close(pre, base, 3e-2, 1e-2, f"preact bn={bn}")
+    _close(got, base * torch.sigmoid(1.702 * base), 3e-2, 1e-2, f"quickgelu bn={bn}")
+    # dgrad: dx[M, Kd] = dy[M, N] . W[N, Kd]  (W read MN-major)
+    Kd = 808
+    dy, wd = _rand((M, 320), seed=24), _rand((320, Kd), 0.05, seed=25)
+    aux = _rand((M, Kd), seed=26)
+    sg = torch.sigmoid(1.702 * aux.float())
+    gref = (dy.float() @ wd.float()) * (sg * (1 + 1.702 * aux.float() * (1 - sg)))
+    cs = torch.zeros(Kd, device="cuda")
+    _close(ops.gemm(dy, wd, b_major=L.MAJOR_MN, epilogue=L.EPI_QUICKGELU_BWD, aux=aux, colsum=cs), gref, 3e-2, 1e-2,
+           f"dgrad quickgelu_bwd bn={bn}")
+    _close(cs, gref.sum(0), 0.5, 1e-2, f"dgrad colsum bn={bn}")
+    # several tiles per CTA (persistent loop, both TMEM stages) at a tall shape
+    M2 = 128 * 300 + 40
+    a2 = _rand((M2, 128), seed=27)
+    w2 = _rand((264, 128), 0.05, seed=28)
+    _close(ops.gemm(a2, w2), a2.float() @ w2.float().t(), 3e-2, 1e-2, f"tall bn={bn}")
+
+
 @pytest.mark.parametrize("M", [1000, 6400, 20000])   # 6400 rows -> 128 x 192 tiles, 20000 rows -> CTA-pair kernel
 def test_gemm_epilogues(ops, M):
     from construction_clip_b200 import lib as L

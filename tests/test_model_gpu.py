@@ -651,3 +651,41 @@ def test_activation_recompute_is_exact():
     for k in g0:
         assert cosine(g1[k].cpu(), g0[k].cpu()) > 0.9999, k
         assert abs(g1[k].norm().item() / g0[k].norm().item() - 1) < 1e-2, k
+
+
+def test_inference_graph_replay_matches_eager():
+    """Small no-grad calls (CLIP/predict.py, parse_coco.py shapes) are captured into a CUDA graph per input shape;
+    the replay must return what the eager launches return, keep doing so when the inputs or the (fp32) weights
+    change, and hand out fresh tensors (not views of the graph's static buffers)."""
+    name = "ViT-B/32"
+    orc = oracle_model(name)
+    m = device_model(name, orc, dtype=torch.float32).eval()
+    img, tok = _inputs(name, 5, 3, 12)
+    img2 = img.flip(0).contiguous()
+    keep = type(m).GRAPH_MAX_ROWS
+    try:
+        type(m).GRAPH_MAX_ROWS = 0
+        with torch.no_grad():
+            ref1, _ = m(img.cuda(), tok.cuda())
+            ref2, _ = m(img2.cuda(), tok.cuda())
+            rfi = m.encode_image(img.cuda())
+        type(m).GRAPH_MAX_ROWS = keep
+        with torch.no_grad():
+            a, at = m(img.cuda(), tok.cuda())      # capture + replay
+            b, _ = m(img2.cuda(), tok.cuda())      # replay with new inputs
+            a_again, _ = m(img.cuda(), tok.cuda())
+            fi = m.encode_image(img.cuda())
+        assert len(m._igraphs) == 2
+        assert torch.allclose(a, ref1, atol=1e-5) and torch.allclose(b, ref2, atol=1e-5) and torch.allclose(fi, rfi, atol=1e-5)
+        assert torch.equal(a, a_again) and a.data_ptr() != a_again.data_ptr() and torch.equal(at, a.t())
+        # weights change (an optimizer step on the fp32 parameters): the next replay must see them
+        with torch.no_grad():
+            m.visual.proj.mul_(1.5)
+            c, _ = m(img.cuda(), tok.cuda())
+        assert not torch.allclose(c, a, atol=1e-3)
+        # under autograd nothing is graphed
+        m.train()
+        lpi, _ = m(img.cuda(), tok.cuda())
+        assert lpi.requires_grad
+    finally:
+        type(m).GRAPH_MAX_ROWS = keep

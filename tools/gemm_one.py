@@ -1,4 +1,4 @@
-"""One GEMM shape, a few launches (for ncu --set full).  usage: gemm_one.py case"""
+"""One GEMM shape, a few launches (for ncu --set full).  usage: gemm_one.py case [rows]"""
 import sys
 import torch
 sys.path.insert(0, ".")
@@ -7,6 +7,8 @@ bf16, f32 = torch.bfloat16, torch.float32
 case = sys.argv[1]
 dev = "cuda"
 M, d = (78848, 512) if case.startswith("txt") else (51200, 768)
+if len(sys.argv) > 2:
+    M = int(sys.argv[2])
 x = torch.randn(M, d, device=dev).to(bf16)
 x4 = torch.randn(M, 4 * d, device=dev).to(bf16)
 xf = torch.randn(M, d, device=dev)

@@ -24,6 +24,11 @@ for STAGE in "$@"; do
         bench2)       B200CLIP_BENCH_VARIANTS=0 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29542 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/${TAG}_bench2.json 2> gpurun_out/${TAG}_bench2.err ;;
         graph128)     timeout 400 python tools/graph_bench.py 128 > gpurun_out/${TAG}_graph128.txt 2>&1 ;;
         graph1024)    timeout 400 python tools/graph_bench.py 1024 > gpurun_out/${TAG}_graph1024.txt 2>&1 ;;
+        cfg1)         timeout 300 python bench.py --config 1 --steps 50 > gpurun_out/${TAG}_cfg1.json 2> gpurun_out/${TAG}_cfg1.err ;;
+        cfg3)         timeout 300 python bench.py --config 3 --steps 3 > gpurun_out/${TAG}_cfg3.json 2> gpurun_out/${TAG}_cfg3.err ;;
+        cfg4)         timeout 300 python bench.py --config 4 --steps 5 > gpurun_out/${TAG}_cfg4.json 2> gpurun_out/${TAG}_cfg4.err ;;
+        cfg5small)    BENCH_PAIRS_PER_GPU=64 timeout 400 python bench.py --config 5 --steps 2 > gpurun_out/${TAG}_cfg5small.json 2> gpurun_out/${TAG}_cfg5small.err ;;
+        cfg5)         timeout 600 python bench.py --config 5 --steps 3 > gpurun_out/${TAG}_cfg5.json 2> gpurun_out/${TAG}_cfg5.err ;;
         smoke)        timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1 ;;
         *)            echo "unknown stage $STAGE" ;;
     esac
