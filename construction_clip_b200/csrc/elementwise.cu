@@ -278,7 +278,18 @@ im2col_kernel(const TIn* __restrict__ img, __nv_bfloat16* __restrict__ cols, int
         if ((p & 7) == 0) {
             for (int px = 0; px < p; px += 8) {
                 float f[8];
-                if constexpr (sizeof(TIn) == 4) {
+                if constexpr (sizeof(TIn) == 1) {   // raw pixels: ToTensor + Normalize fused (clip._transform)
+                    const uint2 u = *reinterpret_cast<const uint2*>(src + px);
+                    const float sc = c == 0 ? 1.0f / (255.0f * 0.26862954f) : (c == 1 ? 1.0f / (255.0f * 0.26130258f) : 1.0f / (255.0f * 0.27577711f));
+                    const float sh = c == 0 ? -0.48145466f / 0.26862954f : (c == 1 ? -0.4578275f / 0.26130258f : -0.40821073f / 0.27577711f);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        f[j] = fmaf(static_cast<float>((u.x >> (8 * j)) & 0xffu), sc, sh);
+                        f[4 + j] = fmaf(static_cast<float>((u.y >> (8 * j)) & 0xffu), sc, sh);
+                    }
+                    *reinterpret_cast<uint4*>(dst + px) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
+                                                                     pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                } else if constexpr (sizeof(TIn) == 4) {
                     const float4 a = *reinterpret_cast<const float4*>(src + px);
                     const float4 bq = *reinterpret_cast<const float4*>(src + px + 4);
                     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
@@ -291,10 +302,15 @@ im2col_kernel(const TIn* __restrict__ img, __nv_bfloat16* __restrict__ cols, int
             }
         } else {
             for (int px = 0; px < p; ++px) {
-                if constexpr (sizeof(TIn) == 4)
+                if constexpr (sizeof(TIn) == 1) {
+                    const float sc = c == 0 ? 1.0f / (255.0f * 0.26862954f) : (c == 1 ? 1.0f / (255.0f * 0.26130258f) : 1.0f / (255.0f * 0.27577711f));
+                    const float sh = c == 0 ? -0.48145466f / 0.26862954f : (c == 1 ? -0.4578275f / 0.26130258f : -0.40821073f / 0.27577711f);
+                    dst[px] = __float2bfloat16_rn(fmaf(static_cast<float>(src[px]), sc, sh));
+                } else if constexpr (sizeof(TIn) == 4) {
                     dst[px] = __float2bfloat16_rn(static_cast<float>(src[px]));
-                else
+                } else {
                     dst[px] = src[px];
+                }
             }
         }
     }
@@ -626,12 +642,17 @@ extern "C" int b200clip_im2col_patch(b200clip_ctx* ctx, const void* image, int i
     const int64_t k = 3 * patch * patch;
     B200_CHECK_ARG(ldcols >= k && ldcols % 8 == 0, "im2col: ldcols=%lld must be >= %lld and a multiple of 8",
                    (long long)ldcols, (long long)k);
-    B200_CHECK_ARG(in_dtype == B200CLIP_DT_BF16 || in_dtype == B200CLIP_DT_F32, "im2col: bad in_dtype");
+    B200_CHECK_ARG(in_dtype == B200CLIP_DT_BF16 || in_dtype == B200CLIP_DT_F32 || in_dtype == B200CLIP_DT_U8,
+                   "im2col: bad in_dtype");
     const int g = static_cast<int>(R / patch);
     const int64_t nseg = B * g * g * 3 * patch;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int grid = grid_for(nseg, 256, ctx->num_sms, 16);
-    if (in_dtype == B200CLIP_DT_F32)
+    if (in_dtype == B200CLIP_DT_U8)
+        im2col_kernel<uint8_t><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(image), static_cast<__nv_bfloat16*>(cols),
+                                                     ldcols, static_cast<int>(B), static_cast<int>(R),
+                                                     static_cast<int>(patch), g);
+    else if (in_dtype == B200CLIP_DT_F32)
         im2col_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(image), static_cast<__nv_bfloat16*>(cols),
                                                    ldcols, static_cast<int>(B), static_cast<int>(R),
                                                    static_cast<int>(patch), g);

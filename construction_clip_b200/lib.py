@@ -17,7 +17,7 @@ LIB_PATH = PKG / "libb200clip.so"
 # enums of include/b200clip.h
 MAJOR_K, MAJOR_MN = 0, 1
 EPI_NONE, EPI_QUICKGELU, EPI_RESIDUAL, EPI_QUICKGELU_BWD = 0, 1, 2, 3
-DT_BF16, DT_F32 = 0, 1
+DT_BF16, DT_F32, DT_U8 = 0, 1, 2
 ABI_VERSION = 1
 
 _p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float

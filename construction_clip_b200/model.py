@@ -324,6 +324,7 @@ class CLIP(nn.Module):
         self._stores = {}
         self._trainer = None          # weakref to the ClipTrainer that owns the master weights, if any
         self._igraphs = {}            # captured no-grad forwards, one per input shape (see _graphed)
+        self._side_stream = None
         self.fp32_check_mode = False  # see set_fp32_check_mode
         self.initialize_parameters()
 
@@ -460,8 +461,23 @@ class CLIP(nn.Module):
         return self._features("text", text).to(self.dtype)
 
     def _forward_eager(self, image, text):
-        img_f = self._features("visual", image)
-        txt_f = self._features("text", text)
+        if torch.is_grad_enabled() or not image.is_cuda:
+            img_f = self._features("visual", image)
+            txt_f = self._features("text", text)
+        else:
+            # inference: the two towers are independent until the logits -> the text tower runs on a second
+            # stream (two parallel branches of the captured graph; small calls are bound by the length of the
+            # dependent kernel chain, not by SM count)
+            cur = torch.cuda.current_stream(image.device)
+            if self._side_stream is None or self._side_stream.device != image.device:
+                self._side_stream = torch.cuda.Stream(device=image.device)
+            side = self._side_stream
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                txt_f = self._features("text", text)
+            img_f = self._features("visual", image)
+            cur.wait_stream(side)
+            txt_f.record_stream(cur)
         return _LogitsFn.apply(img_f, txt_f, self.logit_scale)
 
     def forward(self, image, text):

@@ -264,14 +264,15 @@ def scatter_rows(src, idx, rows):
 # ---------------------------------------------------------------------------------- patch embed
 def im2col_patch(image, patch, ldcols=None):
     B, C, R, R2 = image.shape
-    assert C == 3 and R == R2 and image.is_contiguous() and image.dtype in (bf16, f32)
+    assert C == 3 and R == R2 and image.is_contiguous() and image.dtype in (bf16, f32, torch.uint8)
     g = R // patch
     k = 3 * patch * patch
     if ldcols is None:
         ldcols = (k + 63) // 64 * 64
     cols = torch.empty((B * g * g, ldcols), device=image.device, dtype=bf16)
     ctx, st = _ctx_stream(image)
-    L.check(L.load().b200clip_im2col_patch(ctx, image.data_ptr(), L.DT_F32 if image.dtype == f32 else L.DT_BF16,
+    in_dt = {f32: L.DT_F32, bf16: L.DT_BF16, torch.uint8: L.DT_U8}[image.dtype]   # uint8: raw pixels, Normalize fused
+    L.check(L.load().b200clip_im2col_patch(ctx, image.data_ptr(), in_dt,
                                            cols.data_ptr(), ldcols, B, R, patch, st), "im2col_patch")
     return cols
 

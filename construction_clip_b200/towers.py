@@ -288,7 +288,7 @@ def vision_fwd(W, cfg, image, save: bool, recompute: bool = False):
     B = image.shape[0]
     p, n, d = cfg.vision_patch_size, cfg.vision_tokens, cfg.vision_width
     H = d // 64
-    if image.dtype not in (bf16, f32):
+    if image.dtype not in (bf16, f32, torch.uint8):   # uint8 = raw pixels: ToTensor + Normalize run inside im2col
         image = image.float()
     image = image.contiguous()
     kpad = W["conv1.weight"].shape[1]
@@ -337,7 +337,11 @@ def text_fwd(W, cfg, text, save: bool, rows=None, recompute: bool = False):
     ids = text.to(i32).contiguous()
     saved = TowerSaved(recompute=recompute) if save else None
     cu = None
-    if PACK_TEXT and S <= 128 and (rows is not None or B * S >= PACK_MIN_ROWS):
+    if rows is None and ids.is_cuda and torch.cuda.is_current_stream_capturing():
+        pack = False   # the exact row count needs a host sync: not inside a graph capture (small no-grad forwards)
+    else:
+        pack = PACK_TEXT and S <= 128 and (rows is not None or B * S >= PACK_MIN_ROWS)
+    if pack:
         # keep positions 0 .. EOT of every caption only
         cu, eot = O.text_pack_plan(ids, rows if rows is not None else B * S)
         if rows is None:
@@ -390,6 +394,10 @@ def vision_fwd_f32(W, cfg, image):
     B = image.shape[0]
     p, n, d = cfg.vision_patch_size, cfg.vision_tokens, cfg.vision_width
     kpad = W["conv1.weight"].shape[1]
+    if image.dtype == torch.uint8:   # raw pixels: upstream's ToTensor + Normalize (clip._transform)
+        mean = torch.tensor((0.48145466, 0.4578275, 0.40821073), device=image.device).view(1, 3, 1, 1)
+        std = torch.tensor((0.26862954, 0.26130258, 0.27577711), device=image.device).view(1, 3, 1, 1)
+        image = (image.float() / 255.0 - mean) / std
     cols = O.check_im2col_f32(image.float().contiguous(), p, kpad)
     patch = O.check_gemm_f32(cols, W["conv1.weight"])
     g2 = n - 1

@@ -60,7 +60,7 @@ enum {
     B200CLIP_EPI_QUICKGELU_BWD = 3  /* C = acc * quickgelu'(aux)                            */
 };
 
-enum { B200CLIP_DT_BF16 = 0, B200CLIP_DT_F32 = 1 };
+enum { B200CLIP_DT_BF16 = 0, B200CLIP_DT_F32 = 1, B200CLIP_DT_U8 = 2 /* im2col_patch input only */ };
 
 typedef struct b200clip_ctx b200clip_ctx;
 
@@ -187,7 +187,11 @@ int b200clip_scatter_rows(b200clip_ctx* ctx, const void* src, const int32_t* idx
 
 /* ---- visual.conv1 (Conv2d, kernel = stride = patch, no bias) as im2col + GEMM ---------------------
  * image: [B,3,R,R] bf16 or fp32 (in_dtype) -> cols bf16 [B*g*g, ldcols], ldcols >= 3*p*p (padded
- * columns are zero-filled); column order (c, py, px) matches conv1.weight.view(width, 3*p*p). */
+ * columns are zero-filled); column order (c, py, px) matches conv1.weight.view(width, 3*p*p).
+ * in_dtype B200CLIP_DT_U8: image holds raw 8-bit pixels (the resized / centre-cropped RGB planes) and the
+ * ToTensor + Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711)) steps of
+ * upstream's clip._transform (CLIP/train.py:56 `self.preprocess`) are applied on the fly:
+ *   x = (u / 255 - mean[c]) / std[c]  -- a quarter of the host->device bytes of an fp32 batch. */
 int b200clip_im2col_patch(b200clip_ctx* ctx, const void* image, int in_dtype, void* cols, int64_t ldcols, int64_t B,
                           int64_t R, int64_t patch, void* stream);
 

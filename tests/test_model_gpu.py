@@ -680,7 +680,7 @@ def test_inference_graph_replay_matches_eager():
         assert torch.equal(a, a_again) and a.data_ptr() != a_again.data_ptr() and torch.equal(at, a.t())
         # weights change (an optimizer step on the fp32 parameters): the next replay must see them
         with torch.no_grad():
-            m.visual.proj.mul_(1.5)
+            m.visual.proj.add_(0.05 * torch.randn_like(m.visual.proj))
             c, _ = m(img.cuda(), tok.cuda())
         assert not torch.allclose(c, a, atol=1e-3)
         # under autograd nothing is graphed
@@ -689,3 +689,23 @@ def test_inference_graph_replay_matches_eager():
         assert lpi.requires_grad
     finally:
         type(m).GRAPH_MAX_ROWS = keep
+
+
+@pytest.mark.parametrize("name", ["ViT-B/32", "ViT-L/14"])
+def test_uint8_pixels_with_fused_normalize(name):
+    """uint8 [B,3,R,R] pixels (resized / cropped RGB planes): ToTensor + Normalize of upstream's _transform
+    (CLIP/train.py:56) run inside the im2col kernel -- same features as feeding the normalised fp32 tensor."""
+    from oracle import clip_oracle as O
+    orc = oracle_model(name)
+    m = device_model(name, orc).eval()
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (3, 3, 224, 224), generator=g, dtype=torch.uint8)
+    mean = torch.tensor((0.48145466, 0.4578275, 0.40821073)).view(1, 3, 1, 1)
+    std = torch.tensor((0.26862954, 0.26130258, 0.27577711)).view(1, 3, 1, 1)
+    ref_in = (u8.float() / 255.0 - mean) / std            # what preprocess() hands the reference's DataLoader
+    with torch.no_grad():
+        ref = orc.encode_image(ref_in)
+        a = m.encode_image(u8.cuda())
+        b = m.encode_image(ref_in.cuda())
+    assert cosine_rows(a.float().cpu(), ref).min() >= 0.999
+    assert cosine_rows(a.float().cpu(), b.float().cpu()).min() >= 0.9999
