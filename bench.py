@@ -339,18 +339,34 @@ def run_ours(args):
             traffic = json.load(fh).get("dram_bytes_per_launch")
 
     # ---------------- end to end through the host-facing API (`e2e`) ----------------
-    for i in range(max(2, args.warmup)):
-        trainer.step_from_host(*host[i % n_host], next_batch=host[(i + 1) % n_host])
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        slot = trainer.step_from_host(*host[i % n_host], next_batch=host[(i + 1) % n_host])
-    e1.record()
-    barrier()
-    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    # Host batches in the wire format of a loader that leaves ToTensor + Normalize to the GPU (uint8 [B,3,R,R]
+    # pixels, construction_clip_b200.data.preprocess_uint8; the kernels normalise inside the patch-embedding
+    # im2col) -- a quarter of the bytes of the fp32 tensors upstream's `preprocess` produces.  The fp32 form
+    # (what the reference's DataLoader yields today, CLIP/train.py:56,159) is timed as well: `e2e_fp32_host`.
+    def e2e_leg(batches):
+        for i in range(max(2, args.warmup)):
+            trainer.step_from_host(*batches[i % n_host], next_batch=batches[(i + 1) % n_host])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            slot = trainer.step_from_host(*batches[i % n_host], next_batch=batches[(i + 1) % n_host])
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        _ = float(slot.item())
+        return ms
+
+    host_u8 = []
+    for i in range(n_host):
+        g8 = torch.Generator().manual_seed(SEED + 17 * rank + 1000 * i)
+        host_u8.append((torch.randint(0, 256, (bl, 3, cfg.image_resolution, cfg.image_resolution), generator=g8,
+                                      dtype=torch.uint8).pin_memory(), host[i][1]))
+    e2e_ms = e2e_leg(host_u8)
     e2e_value = GLOBAL_BATCH * args.steps / (e2e_ms * 1e-3)
-    _ = float(slot.item())
+    h2d_u8 = host_u8[0][0].numel() + host_u8[0][1].numel() * 4
+    e2e32_ms = e2e_leg(host)
+    e2e32_value = GLOBAL_BATCH * args.steps / (e2e32_ms * 1e-3)
 
     def shutdown():
         # Drop captured graphs (they hold NCCL kernels) BEFORE the communicator goes away, and leave
@@ -426,8 +442,13 @@ def run_ours(args):
             "step_executed_tflops_per_gpu": value / world * (exec_flops_step / bl) / 1e12,
             "step_executed_frac_of_bf16_burst_peak": value / world * (exec_flops_step / bl) / 1e12 / peaks["bf16_burst"],
         },
-        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": 4,
-                "ms_per_step": e2e_ms / args.steps},
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_u8, "d2h_bytes_per_step": 4,
+                "ms_per_step": e2e_ms / args.steps,
+                "host_format": "pinned uint8 [B,3,224,224] pixels + int32 [B,77] tokens per rank; ToTensor + Normalize fused "
+                               "into the patch-embedding im2col (construction_clip_b200.data.preprocess_uint8)"},
+        "e2e_fp32_host": {"value": e2e32_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes,
+                          "d2h_bytes_per_step": 4, "ms_per_step": e2e32_ms / args.steps,
+                          "host_format": "pinned fp32 [B,3,224,224] normalised tensors (upstream preprocess) + int32 tokens"},
         "gpu_launches": launches,
         "clocks": clocks,
         "variants": variants,

@@ -15,6 +15,11 @@ Differences from upstream, all forced by the environment and documented in DESIG
     inference / ClipTrainer with its own fp32 master weights).  There is no CPU execution path --
     `device="cpu"` builds the module (state_dict round trips work) but calling it raises.
   * ViT models only (BASELINE config 4: "RN-free"); `jit=True` is not supported.
+
+
+Attribution: the algorithm, constants and public names here follow openai/CLIP's `clip/clip.py (`tokenize`, `_transform`, `load`)` (MIT License,
+Copyright (c) 2021 OpenAI) -- byte-exact behaviour is the contract of this boundary (token ids, pixel
+normalisation constants); the file is a re-implementation kept under the same MIT terms.
 """
 from __future__ import annotations
 

@@ -3,6 +3,11 @@
 The merge table `bpe_simple_vocab_16e6.txt.gz` is upstream data that is NOT in this image and
 cannot be downloaded (no network).  Point CLIP_BPE_PATH at it (or drop it next to this file).
 Without it `clip.tokenize` raises; callers that already hold token ids are unaffected.
+
+
+Attribution: the algorithm, constants and public names here follow openai/CLIP's `clip/simple_tokenizer.py` (MIT License,
+Copyright (c) 2021 OpenAI) -- byte-exact behaviour is the contract of this boundary (token ids, pixel
+normalisation constants); the file is a re-implementation kept under the same MIT terms.
 """
 from __future__ import annotations
 

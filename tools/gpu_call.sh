@@ -29,6 +29,10 @@ for STAGE in "$@"; do
         cfg4)         timeout 300 python bench.py --config 4 --steps 5 > gpurun_out/${TAG}_cfg4.json 2> gpurun_out/${TAG}_cfg4.err ;;
         cfg5small)    BENCH_PAIRS_PER_GPU=64 timeout 400 python bench.py --config 5 --steps 2 > gpurun_out/${TAG}_cfg5small.json 2> gpurun_out/${TAG}_cfg5small.err ;;
         cfg5)         timeout 600 python bench.py --config 5 --steps 3 > gpurun_out/${TAG}_cfg5.json 2> gpurun_out/${TAG}_cfg5.err ;;
+        dist8)        timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29561 tools/dist_check.py > gpurun_out/${TAG}_dist8.log 2>&1 ;;
+        bench8)       B200CLIP_BENCH_VARIANTS=0 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29562 bench.py --gpus 8 --steps 20 --warmup 3 > gpurun_out/${TAG}_bench8.json 2> gpurun_out/${TAG}_bench8.err ;;
+        bench4)       B200CLIP_BENCH_VARIANTS=0 timeout 500 python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29563 bench.py --gpus 4 --steps 10 --warmup 3 > gpurun_out/${TAG}_bench4.json 2> gpurun_out/${TAG}_bench4.err ;;
+        cfg5x8)       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29564 bench.py --gpus 8 --config 5 --steps 3 --warmup 3 > gpurun_out/${TAG}_cfg5x8.json 2> gpurun_out/${TAG}_cfg5x8.err ;;
         smoke)        timeout 300 python __graft_entry__.py smoke > gpurun_out/${TAG}_smoke.log 2>&1 ;;
         *)            echo "unknown stage $STAGE" ;;
     esac
