@@ -1,0 +1,22 @@
+#!/bin/bash
+# bench.py at N GPUs under several NCCL channel settings (how much do the overlapped collectives disturb the
+# persistent GEMMs?).  usage: tools/nccl_variants.sh <ngpus> <tag>
+N=$1; TAG=$2
+run() {
+    name=$1; shift
+    env "$@" B200CLIP_BENCH_VARIANTS=0 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N \
+        --master-addr 127.0.0.1 --master-port $((29600 + RANDOM % 300)) bench.py --gpus $N --steps 20 --warmup 3 \
+        > gpurun_out/${TAG}_${name}.json 2> gpurun_out/${TAG}_${name}.err
+    python - <<PY
+import json
+try:
+    d = json.load(open("gpurun_out/${TAG}_${name}.json"))
+    print("${name}", round(d["value"]), round(d["ms_per_step"], 3), "e2e", round(d["e2e"]["value"]), "e2e32", round(d["e2e_fp32_host"]["value"]))
+except Exception as e:
+    print("${name} failed", e)
+PY
+}
+run base X=1
+run ctas4 NCCL_MAX_CTAS=4
+run ctas8 NCCL_MAX_CTAS=8
+run ctas16 NCCL_MAX_CTAS=16
