@@ -465,8 +465,9 @@ __global__ void cast_bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ src, f
 // Unlike torch.optim.AdamW, eps is added to the UN-corrected sqrt(v) (an effective eps 1/sqrt(1-b2^t) times larger,
 // ~32x at t = 1) and the decoupled decay is applied after the update with the plain lr.
 // fp32 master weights + bf16 shadow copy.
+template <typename TG>   // gradient storage: fp32 (flat accumulators) or bf16 (the wire format of the sharded reduce-scatter)
 __global__ void __launch_bounds__(256)
-adamw_kernel(float* __restrict__ master, __nv_bfloat16* __restrict__ param, const float* __restrict__ grad,
+adamw_kernel(float* __restrict__ master, __nv_bfloat16* __restrict__ param, const TG* __restrict__ grad,
              float* __restrict__ m, float* __restrict__ v, int64_t n, float lr, float beta1, float beta2, float eps,
              float wd, float grad_scale, float bc1, float bc2, const float* __restrict__ hyper) {
     if (hyper != nullptr) {  // step-dependent scalars from device memory (CUDA-graph replay)
@@ -477,7 +478,11 @@ adamw_kernel(float* __restrict__ master, __nv_bfloat16* __restrict__ param, cons
     const float step_size = lr * sqrtf(bc2) / bc1;
     const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
-        const float g = grad[i] * grad_scale;
+        float g;
+        if constexpr (sizeof(TG) == 2)
+            g = __bfloat162float(grad[i]) * grad_scale;
+        else
+            g = grad[i] * grad_scale;
         float p = master[i];
         const float mi = beta1 * m[i] + (1.f - beta1) * g;
         const float vi = beta2 * v[i] + (1.f - beta2) * g * g;
@@ -763,9 +768,23 @@ extern "C" int b200clip_adamw(b200clip_ctx* ctx, float* master, void* param_bf16
     B200_CHECK_ARG(master && grad && m && v && n > 0 && (step > 0 || hyper_dev), "adamw: bad argument");
     const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
     const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
-    adamw_kernel<<<grid_for(n, 256, ctx->num_sms, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    adamw_kernel<float><<<grid_for(n, 256, ctx->num_sms, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         master, static_cast<__nv_bfloat16*>(param_bf16), grad, m, v, n, lr, beta1, beta2, eps, weight_decay, grad_scale,
         bc1, bc2, hyper_dev);
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+extern "C" int b200clip_adamw_g16(b200clip_ctx* ctx, float* master, void* param_bf16, const void* grad_bf16, float* m,
+                                  float* v, int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay,
+                                  float grad_scale, int64_t step, const float* hyper_dev, void* stream) {
+    B200_CHECK_CTX(ctx);
+    B200_CHECK_ARG(master && grad_bf16 && m && v && n > 0 && (step > 0 || hyper_dev), "adamw_g16: bad argument");
+    const float bc1 = 1.f - powf(beta1, static_cast<float>(step));
+    const float bc2 = 1.f - powf(beta2, static_cast<float>(step));
+    adamw_kernel<__nv_bfloat16><<<grid_for(n, 256, ctx->num_sms, 16), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        master, static_cast<__nv_bfloat16*>(param_bf16), static_cast<const __nv_bfloat16*>(grad_bf16), m, v, n, lr, beta1,
+        beta2, eps, weight_decay, grad_scale, bc1, bc2, hyper_dev);
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -48,8 +48,19 @@ constexpr int UMMA_K = 16;        // fixed for 16-bit inputs
 #ifndef B200_EPI_EARLY_RELEASE
 #define B200_EPI_EARLY_RELEASE 0  // hand the TMEM stage back after the last TMEM load, not the last store
 #endif
-constexpr int kEpiWarps = 8;       // two warps per TMEM lane quadrant, each takes half of the tile's columns
+// Epilogue warps: kEpiParts per TMEM lane quadrant, each takes a share of the tile's 32-column blocks.
+// Measured with 12 warps (-DB200_EPI_WARPS=12: 3 column shares, one operand stage less to pay for their staging
+// tiles, 128 registers per thread), same box, ViT-B/32 layer shapes at 1024 pairs: per-layer total 2730 us against
+// 2682 us with 8 -- worse on 22 of 24 shapes (c_fc fwd 235 vs 227 us, out_proj fwd 93 vs 87), better only on the
+// text c_proj dgrad (127 vs 137).  The fat epilogues are not short of warps.
+#ifndef B200_EPI_WARPS
+#define B200_EPI_WARPS 8
+#endif
+constexpr int kEpiWarps = B200_EPI_WARPS;
+constexpr int kEpiParts = kEpiWarps / 4;
+static_assert(kEpiWarps % 4 == 0 && kEpiParts >= 2 && kEpiParts <= 4, "epilogue warps come in groups of four (TMEM lane quadrants)");
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
+constexpr int kSmemBudget = 227 * 1024;
 constexpr int kStageBytesA = BM * BK * 2;  // 16 KB
 constexpr int kEpiStageBytes = 32 * 128;   // per-warp staging: 32 rows x 128 B, XOR-swizzled
 
@@ -64,11 +75,12 @@ struct GemmCfg {
     static constexpr int kBNSmem = (BN + 63) / 64 * 64;
     static constexpr int kStageBytesB = kBNSmem * BK * 2;
     static constexpr int kStageBytes = kStageBytesA + kStageBytesB;
-    static constexpr int kStages = (kBNSmem >= 192) ? 4 : 6;
+    static constexpr int kFit = (kSmemBudget - 1024 - kEpiWarps * kEpiStageBytes) / kStageBytes;  // ring depth that fits
+    static constexpr int kCap = (kBNSmem >= 192) ? 4 : 6;
+    static constexpr int kStages = kFit < kCap ? kFit : kCap;
+    static_assert(kStages >= 3, "operand ring too shallow");
     static constexpr int kTmemCols = (2 * BN > 256) ? 512 : 256;  // two accumulator stages (power of two)
     static constexpr int kSmemBytes = kStages * kStageBytes + kEpiWarps * kEpiStageBytes + 1024;  // + align slack
-    static constexpr int kBlocks = BN / 32;           // 32-column epilogue blocks per tile
-    static constexpr int kBlocks0 = (kBlocks + 1) / 2;  // column half 0 (warps 2-5) drains these, half 1 the rest
 };
 
 struct GemmParams {
@@ -397,7 +409,7 @@ template <int BN, int EPI, bool OUT_F32, bool ATOMIC, bool PAIR = false>
 __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
                                            uint64_t* tmem_empty_bar, uint8_t* stg, int warp, int lane, int num_work) {
     const int quad = warp & 3;         // TMEM lane quadrant this warp may access
-    const int half = (warp - 2) >> 2;  // which half of the tile's columns this warp drains
+    const int part = (warp - 2) >> 2;  // which share of the tile's columns this warp drains
     const float scale = (p.scale != nullptr) ? __ldg(p.scale) : 1.0f;
     int as = 0;
     uint32_t aphase = 0;
@@ -411,9 +423,11 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
     // mainloop's operand loads: up to 2.4x slower).
     constexpr bool kHasAux = (EPI == B200CLIP_EPI_QUICKGELU_BWD);
     constexpr int kAuxElem = (EPI == B200CLIP_EPI_RESIDUAL && OUT_F32) ? 4 : 2;
-    constexpr int kBlocks0 = (BN / 32 + 1) / 2;                     // blocks of column half 0
-    const int blk0 = half ? kBlocks0 : 0;                           // first block of this warp's half
-    const int nblk_half = half ? BN / 32 - kBlocks0 : kBlocks0;     // blocks this warp drains per tile
+    constexpr int kBlocks = BN / 32, kBase = kBlocks / kEpiParts, kRem = kBlocks % kEpiParts;
+    constexpr int kBlocks0 = kBase + (kRem ? 1 : 0);                            // the largest share (<= 4)
+    static_assert(kBlocks0 <= 4, "drain_tile handles at most four blocks per warp");
+    const int blk0 = part * kBase + (part < kRem ? part : kRem);                 // first block of this warp's share
+    const int nblk_half = kBase + (part < kRem ? 1 : 0);                         // blocks this warp drains per tile
     auto prefetch_aux = [&](int wq) {
         if constexpr (kHasAux && B200_EPI_AUX_PREFETCH) {
             if (wq < num_work) {
@@ -635,7 +649,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // accumulator-full barriers are signalled in both CTAs with a multicast tcgen05.commit, and both
 // epilogues release the accumulator on the leader's barrier.
 constexpr int kStageBytesPair = 2 * (BM * BK * 2);  // A 16 KB + half of B 16 KB
-constexpr int kStagesPair = 6;
+constexpr int kStagesPairFit = (kSmemBudget - 1024 - kEpiWarps * kEpiStageBytes) / kStageBytesPair;
+constexpr int kStagesPair = kStagesPairFit < 6 ? kStagesPairFit : 6;
 constexpr int kSmemBytesPair = kStagesPair * kStageBytesPair + kEpiWarps * kEpiStageBytes + 1024;
 
 template <bool A_MN, bool B_MN>

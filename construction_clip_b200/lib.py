@@ -59,6 +59,7 @@ SIGNATURES = {
     "b200clip_check_attn_fwd_f32": [_p, _p, _p, _l, _l, _l, _i, _p],
     "b200clip_check_im2col_f32": [_p, _p, _p, _l, _l, _l, _l, _p],
     "b200clip_adamw": [_p, _p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _l, _p, _p],
+    "b200clip_adamw_g16": [_p, _p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _l, _p, _p],
 }
 _RESTYPES = {"b200clip_last_error": C.c_char_p, "b200clip_launch_count": C.c_uint64, "b200clip_clip_loss_workspace_bytes": C.c_int64}
 

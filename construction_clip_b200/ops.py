@@ -383,9 +383,9 @@ def clip_loss_bwd(img_all, txt_all, logit_scale, lse_i_all, lse_t_all, grad_out,
 
 def adamw(master, param_bf16, grad, m, v, *, lr, beta1, beta2, eps, weight_decay, grad_scale, step, hyper=None):
     ctx, st = _ctx_stream(master)
-    L.check(L.load().b200clip_adamw(ctx, master.data_ptr(), _ptr(param_bf16), grad.data_ptr(), m.data_ptr(),
-                                    v.data_ptr(), master.numel(), lr, beta1, beta2, eps, weight_decay, grad_scale,
-                                    step, _ptr(hyper), st), "adamw")
+    fn = L.load().b200clip_adamw_g16 if grad.dtype == bf16 else L.load().b200clip_adamw   # bf16: the reduce-scatter wire format
+    L.check(fn(ctx, master.data_ptr(), _ptr(param_bf16), grad.data_ptr(), m.data_ptr(), v.data_ptr(), master.numel(), lr,
+               beta1, beta2, eps, weight_decay, grad_scale, step, _ptr(hyper), st), "adamw")
 
 
 # ------------------------------------------------------------------------------ fp32 check mode

@@ -191,6 +191,12 @@ class ClipTrainer:
         # points of the backward pass (layers finish last-to-first); a chunk's collectives + update run
         # on a side stream as soon as it is final, under the rest of the backward (see _plan_chunks).
         self.sharded = bool(shard_optimizer) and self.world > 1
+        # wire format of the sharded gradient reduce-scatter: bf16 halves the NVLink bytes (605 -> 302 MB per step for
+        # ViT-B/32) and the optimiser's gradient read; the fp32 accumulators are cast chunk by chunk right before the
+        # collective.  B200CLIP_GRAD_WIRE=fp32 keeps the exact fp32 sum.
+        import os as _os
+        self.grad_wire_bf16 = self.sharded and _os.environ.get("B200CLIP_GRAD_WIRE", "bf16") != "fp32"
+        self.gwire = {}
         self.grads, self.master, self.m, self.v, self.chunks, self.chunk_ready = {}, {}, {}, {}, {}, {}
         self._comm_streams = {}
         # the two towers' collectives are issued from two streams; a second communicator keeps the text
@@ -202,6 +208,8 @@ class ClipTrainer:
         for k, st in self.stores.items():
             st.sync()
             self.grads[k] = torch.zeros(st.total, device=self.device, dtype=f32)
+            if self.grad_wire_bf16:
+                self.gwire[k] = torch.zeros(st.total, device=self.device, dtype=bf16)
             ranges = _plan_chunks(st, self.world) if self.sharded else [(0, st.total, -1)]
             chunks, moff = [], 0
             for a, b, ready in ranges:
@@ -388,9 +396,16 @@ class ClipTrainer:
                 continue
             lo = a + self.rank * n
             grp = self._tower_group[k]
+            gs = g[lo:lo + n]
             if not reduced:
-                dist.reduce_scatter_tensor(g[lo:lo + n], g[a:b], group=grp)
-            O.adamw(self.master[k][moff:moff + n], st.w[lo:lo + n], g[lo:lo + n], self.m[k][moff:moff + n],
+                if self.grad_wire_bf16:
+                    gw = self.gwire[k]
+                    O.cast_f32_to_bf16(g[a:b], gw[a:b])
+                    dist.reduce_scatter_tensor(gw[lo:lo + n], gw[a:b], group=grp)
+                    gs = gw[lo:lo + n]
+                else:
+                    dist.reduce_scatter_tensor(gs, g[a:b], group=grp)
+            O.adamw(self.master[k][moff:moff + n], st.w[lo:lo + n], gs, self.m[k][moff:moff + n],
                     self.v[k][moff:moff + n], **self._adam_args(hyper))
             dist.all_gather_into_tensor(st.w[a:b], st.w[lo:lo + n], group=grp)
 

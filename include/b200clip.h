@@ -278,6 +278,13 @@ int b200clip_adamw(b200clip_ctx* ctx, float* master, void* param_bf16, const flo
                    int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                    int64_t step, const float* hyper_dev, void* stream);
 
+/* Same update with the gradient stored in bf16: the wire format of the sharded (ZeRO-1) gradient reduce-scatter --
+ * each rank casts its flat fp32 gradient chunk to bf16, the chunk is reduce-scattered in bf16 (half the NVLink
+ * bytes) and this rank's shard is consumed directly. */
+int b200clip_adamw_g16(b200clip_ctx* ctx, float* master, void* param_bf16, const void* grad_bf16, float* m, float* v,
+                       int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
+                       int64_t step, const float* hyper_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
