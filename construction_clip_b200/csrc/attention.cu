@@ -38,6 +38,7 @@ struct AttnParams {
     // The kernels zero-fill them in their output (out_ld elements per row) so that everything downstream
     // (row-wise GEMMs / LayerNorms, and the token-reductions of the weight gradients) sees finite zeros.
     int total_rows, out_ld;
+    int kvb;  // attn_fwd_long_kernel: rows of a KV block (multiple of 16, <= kLongKvbMax)
 };
 
 // zero-fill of the surplus rows of a packed output (see AttnParams::total_rows); the whole grid takes part
@@ -297,27 +298,37 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
 
 // ------------------------------------------------------------------------------------------------
 // Forward for sequences longer than one tile (ViT-B/16: 197, ViT-L/14: 257, ViT-L/14@336: 577 tokens):
-// one CTA per (sample, head, 128-row query block), KV streamed in 128-row blocks with the online
-// softmax recurrence; S_j = Q K_j^T and P_j V_j run on the tensor core, the running output lives in
-// registers (64 fp32 per thread = one row) and is rescaled by exp2(m_old - m_new) per block.
+// one CTA per (sample, head, 128-row query block), KV streamed in blocks with the online softmax
+// recurrence; S_j = Q K_j^T and P_j V_j run on the tensor core, the running output lives in registers
+// (64 fp32 per thread = one row) and is rescaled by exp2(m_old - m_new) per block.
+// Round 2: (a) the KV block height is chosen per sequence length (p.kvb, a multiple of 16 up to 160) so that
+// the blocks are evenly filled -- 257 tokens are 2 blocks of 144 (not 128 + 128 + 1), 577 are 4 of 160 (not 5);
+// (b) the next block's K is requested as soon as S_j = Q K_j^T has retired and its V as soon as P_j V_j has,
+// so the loads run under the softmax / the next score MMA instead of in front of them (no extra shared
+// memory: each tile is simply re-filled the moment its last reader is done); (c) ex2.approx instead of exp2f.
+constexpr int kLongKvbMax = 160;                       // 2 CTAs / SM: Q 16 KB + K, V 20 KB each + P 3 x 16 KB
+constexpr int kLongSmem = kTile + 2 * kLongKvbMax * 128 + 3 * kTile + 1024;
 __global__ void __launch_bounds__(kAttnThreads)
-attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) {
+attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
+                     const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_q, bar_kv, bar_mma;
+    __shared__ uint64_t bar_q, bar_k, bar_v, bar_mma;
     __shared__ uint32_t tmem_slot;
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + kTile;
-    uint8_t* sV = sK + kTile;
-    uint8_t* sP = sV + kTile;  // two 64-column tiles
-    constexpr int kTmemCols = 256;  // [0,128) scores, [128,192) P V
+    uint8_t* sV = sK + kLongKvbMax * 128;
+    uint8_t* sP = sV + kLongKvbMax * 128;  // up to three 64-column tiles of 128 rows
+    constexpr int kTmemCols = 256;          // [0,160) scores, [192,256) P V
 
     const int warp = threadIdx.x >> 5;
     const int r = threadIdx.x;
     if (threadIdx.x == 0) {
-        prefetch_tmap(&tm_qkv);
+        prefetch_tmap(&tm_q);
+        prefetch_tmap(&tm_kv);
         mbar_init(&bar_q, 1);
-        mbar_init(&bar_kv, 1);
+        mbar_init(&bar_k, 1);
+        mbar_init(&bar_v, 1);
         mbar_init(&bar_mma, 1);
         fence_barrier_init();
     }
@@ -328,10 +339,11 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParam
     const uint32_t tmem = tmem_slot;
     const uint32_t trow = tmem + (static_cast<uint32_t>(warp * 32) << 16);
 
-    const int S = p.S, H = p.H;
+    const int S = p.S, H = p.H, KVB = p.kvb;
     const int d = H * 64;
     const int nqb = (S + 127) / 128;
-    const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    const uint32_t kv_bytes = static_cast<uint32_t>(KVB) * 128u;
+    const uint32_t idesc_s = make_idesc_bf16(128, KVB, 0, 0);
     const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
     const float sc = 0.125f * kLog2e;
     const int num_work = p.B * H * nqb;
@@ -342,22 +354,24 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParam
         const int b = bh / H, h = bh % H;
         const int q0 = qb * 128;
         const int row = q0 + r;  // query index inside the sample
-        if (threadIdx.x == 0) {
+        const int kv_end = p.causal ? min(S, q0 + 128) : S;
+        if (threadIdx.x == 0) {   // Q and the first K / V block (every tile is free: the previous item ended with a block sync)
             mbar_arrive_expect_tx(&bar_q, kTile);
-            tma_load_2d(sQ, &tm_qkv, &bar_q, h * 64, b * S + q0);
+            tma_load_2d(sQ, &tm_q, &bar_q, h * 64, b * S + q0);
+            mbar_arrive_expect_tx(&bar_k, kv_bytes);
+            tma_load_2d(sK, &tm_kv, &bar_k, d + h * 64, b * S);
+            mbar_arrive_expect_tx(&bar_v, kv_bytes);
+            tma_load_2d(sV, &tm_kv, &bar_v, 2 * d + h * 64, b * S);
         }
         float m = -INFINITY, l = 0.f;
         float o[64];
 #pragma unroll
         for (int c = 0; c < 64; ++c) o[c] = 0.f;
-        const int kv_end = p.causal ? min(S, q0 + 128) : S;
-        for (int k0 = 0; k0 < kv_end; k0 += 128, ++kv_it) {
+        for (int k0 = 0; k0 < kv_end; k0 += KVB, ++kv_it) {
+            const bool more = k0 + KVB < kv_end;
             if (threadIdx.x == 0) {
-                mbar_arrive_expect_tx(&bar_kv, 2 * kTile);
-                tma_load_2d(sK, &tm_qkv, &bar_kv, d + h * 64, b * S + k0);
-                tma_load_2d(sV, &tm_qkv, &bar_kv, 2 * d + h * 64, b * S + k0);
                 if (k0 == 0) mbar_wait(&bar_q, it & 1u);
-                mbar_wait(&bar_kv, kv_it & 1u);
+                mbar_wait(&bar_k, kv_it & 1u);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
@@ -366,35 +380,51 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParam
                 umma_commit(&bar_mma);
             }
             mbar_wait(&bar_mma, 0u);
+            if (threadIdx.x == 0 && more) {   // K_j has been consumed: fetch K_{j+1} under the softmax
+                mbar_arrive_expect_tx(&bar_k, kv_bytes);
+                tma_load_2d(sK, &tm_kv, &bar_k, d + h * 64, b * S + k0 + KVB);
+            }
             __syncwarp();
             tc_fence_after();
             float mx = m;
-            for (int c0 = 0; c0 < 128; c0 += 16) {
+            for (int c0 = 0; c0 < KVB; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld_32x16(trow + c0, v);
                 tmem_ld_wait();
+                if (k0 + c0 + 16 <= S && !p.causal) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int col = k0 + c0 + j;
-                    if (col < S && !(p.causal && col > row)) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int col = k0 + c0 + j;
+                        if (col < S && !(p.causal && col > row)) mx = fmaxf(mx, __uint_as_float(v[j]));
+                    }
                 }
             }
             // a fully masked row (padding rows past S when causal) keeps mx = -inf: use 0 to stay finite
             const float mref = (mx == -INFINITY) ? 0.f : mx;
-            const float alpha = exp2f((m - mref) * sc);  // m = -inf -> 0
+            const float alpha = (m == -INFINITY) ? 0.f : ex2_fast((m - mref) * sc);
+            const float msc = mref * sc;
             float sum = 0.f;
-            for (int c0 = 0; c0 < 128; c0 += 16) {
+            for (int c0 = 0; c0 < KVB; c0 += 16) {
                 uint32_t v[16];
                 tmem_ld_32x16(trow + c0, v);
                 tmem_ld_wait();
                 float e[16];
+                if (k0 + c0 + 16 <= S && !p.causal) {
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const int col = k0 + c0 + j;
-                    const bool msk = col >= S || (p.causal && col > row);
-                    e[j] = msk ? 0.f : exp2f((__uint_as_float(v[j]) - mref) * sc);
-                    sum += e[j];
+                    for (int j = 0; j < 16; ++j) e[j] = ex2_fast(fmaf(__uint_as_float(v[j]), sc, -msc));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const int col = k0 + c0 + j;
+                        const bool msk = col >= S || (p.causal && col > row);
+                        e[j] = msk ? 0.f : ex2_fast(fmaf(__uint_as_float(v[j]), sc, -msc));
+                    }
                 }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) sum += e[j];
                 *reinterpret_cast<uint4*>(p_chunk(sP, kTile, r, c0 >> 3)) =
                     make_uint4(pack_bf16(e[0], e[1]), pack_bf16(e[2], e[3]), pack_bf16(e[4], e[5]), pack_bf16(e[6], e[7]));
                 *reinterpret_cast<uint4*>(p_chunk(sP, kTile, r, (c0 >> 3) + 1)) =
@@ -406,26 +436,31 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParam
             tc_fence_before();
             __syncthreads();
             if (threadIdx.x == 0) {
+                mbar_wait(&bar_v, kv_it & 1u);
                 tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_bf16(tmem + 128, make_smem_desc_sw128(smem_u32(sP) + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
+                const int ksteps = KVB >> 4;
+                for (int k = 0; k < ksteps; ++k)
+                    umma_bf16(tmem + 192, make_smem_desc_sw128(smem_u32(sP) + (k >> 2) * kTile + (k & 3) * 32, 16, 1024),
                               make_smem_desc_sw128(smem_u32(sV) + k * 2048, 8192, 1024), idesc_o, k > 0 ? 1u : 0u);
                 umma_commit(&bar_mma);
             }
             mbar_wait(&bar_mma, 1u);
+            if (threadIdx.x == 0 && more) {   // V_j has been consumed: fetch V_{j+1} under the next score MMA + softmax
+                mbar_arrive_expect_tx(&bar_v, kv_bytes);
+                tma_load_2d(sV, &tm_kv, &bar_v, 2 * d + h * 64, b * S + k0 + KVB);
+            }
             __syncwarp();
             tc_fence_after();
 #pragma unroll
             for (int c0 = 0; c0 < 64; c0 += 32) {
                 uint32_t v[32];
-                tmem_ld_32x32(trow + 128 + c0, v);
+                tmem_ld_32x32(trow + 192 + c0, v);
                 tmem_ld_wait();
 #pragma unroll
                 for (int j = 0; j < 32; ++j) o[c0 + j] = fmaf(o[c0 + j], alpha, __uint_as_float(v[j]));
             }
             tc_fence_before();
-            __syncthreads();  // K / V / P and both accumulators are reused by the next block
+            __syncthreads();  // P and both accumulators are reused by the next block
             tc_fence_after();
         }
         if (row < S) {
@@ -956,7 +991,7 @@ int init_attention(b200clip_ctx*) {
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, fwd_smem(true, 128));
     if (e == cudaSuccess)
-        e = cudaFuncSetAttribute(attn_fwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * kTile + 1024);
+        e = cudaFuncSetAttribute(attn_fwd_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kLongSmem);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(attn_bwd_long_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * kTile + 1024);
     if (e == cudaSuccess)
@@ -1012,9 +1047,14 @@ extern "C" int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, 
     if (rc) return rc;
     B200_CHECK_ARG((reinterpret_cast<uintptr_t>(out) & 15) == 0, "attention: out not 16-byte aligned");
     if (S > 128) {
-        CUtensorMap tml;
+        // KV block height: the fewest blocks of at most kLongKvbMax rows, evenly filled (257 -> 2 x 144, 577 -> 4 x 160)
+        const int nkb = static_cast<int>((S + kLongKvbMax - 1) / kLongKvbMax);
+        const int kvb = static_cast<int>(((S + nkb - 1) / nkb + 15) / 16 * 16);
+        CUtensorMap tml, tmkv;
         if ((rc = make_tmap_bf16_2d(ctx, &tml, qkv, 3 * H * 64, B * S, 3 * H * 64, 64, 128))) return rc;
+        if ((rc = make_tmap_bf16_2d(ctx, &tmkv, qkv, 3 * H * 64, B * S, 3 * H * 64, 64, static_cast<uint32_t>(kvb)))) return rc;
         AttnParams pl{};
+        pl.kvb = kvb;
         pl.out = static_cast<__nv_bfloat16*>(out);
         pl.lse = lse;
         pl.B = static_cast<int>(B);
@@ -1025,7 +1065,7 @@ extern "C" int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, 
         const int64_t work_l = B * H * ((S + 127) / 128);
         B200_CHECK_ARG(work_l < (1ll << 31), "attention: extent too large");
         const int grid_l = static_cast<int>(work_l < ctx->num_sms * 2 ? work_l : ctx->num_sms * 2);
-        attn_fwd_long_kernel<<<grid_l, kAttnThreads, 5 * kTile + 1024, static_cast<cudaStream_t>(stream)>>>(tml, pl);
+        attn_fwd_long_kernel<<<grid_l, kAttnThreads, kLongSmem, static_cast<cudaStream_t>(stream)>>>(tml, tmkv, pl);
         B200_LAUNCH_CHECK();
         return 0;
     }
