@@ -39,6 +39,8 @@ struct AttnParams {
     // (row-wise GEMMs / LayerNorms, and the token-reductions of the weight gradients) sees finite zeros.
     int total_rows, out_ld;
     int kvb;  // attn_fwd_long_kernel: rows of a KV block (multiple of 16, <= kLongKvbMax)
+    const __nv_bfloat16* qkv;  // attn_fwd_long_kernel: the packed in_proj output (SIMT tail rows read it directly)
+    int tail_max;              // attn_fwd_long_kernel: at most this many rows past the last full query block go to the SIMT tail
 };
 
 // zero-fill of the surplus rows of a packed output (see AttnParams::total_rows); the whole grid takes part
@@ -307,6 +309,112 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnParams p) 
 // so the loads run under the softmax / the next score MMA instead of in front of them (no extra shared
 // memory: each tile is simply re-filled the moment its last reader is done); (c) ex2.approx instead of exp2f.
 constexpr int kLongKvbMax = 160;                       // 2 CTAs / SM: Q 16 KB + K, V 20 KB each + P 3 x 16 KB
+constexpr int kLongTailMax = 8;                        // rows past the last full query block handled by the SIMT tail
+
+// softmax(q k^T / 8) v for `n` query rows [q_first, q_first + n) of (sample b, head h), all S keys (no mask: the
+// long kernels serve the vision tower), straight from global memory (L2: this CTA has just streamed the same K / V).
+// 128 threads; thread t owns keys t, t + 128, ...  s_red: 4 x 66 floats.
+__device__ __forceinline__ void long_tail_rows(const AttnParams& p, int b, int h, int q_first, int n, float* s_red) {
+    const int S = p.S, d = p.H * 64;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float sc = 0.125f * kLog2e;
+    const __nv_bfloat16* base = p.qkv + static_cast<int64_t>(b) * S * (3 * d) + h * 64;
+    for (int i = 0; i < n; ++i) {
+        const int row = q_first + i;
+        const __nv_bfloat16* q = base + static_cast<int64_t>(row) * (3 * d);
+        float qf[64];
+#pragma unroll
+        for (int c = 0; c < 64; c += 8) {
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(q + c));
+            const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_bf16(wv[j]);
+                qf[c + 2 * j] = f.x;
+                qf[c + 2 * j + 1] = f.y;
+            }
+        }
+        // scores of this thread's keys (at most 5 for S <= 640), running max
+        float sv[5];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const int key = threadIdx.x + 128 * t;
+            sv[t] = -INFINITY;
+            if (key < S) {
+                const __nv_bfloat16* k = base + static_cast<int64_t>(key) * (3 * d) + d;
+                float acc = 0.f;
+#pragma unroll
+                for (int c = 0; c < 64; c += 8) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(k + c));
+                    const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack_bf16(wv[j]);
+                        acc = fmaf(qf[c + 2 * j], f.x, acc);
+                        acc = fmaf(qf[c + 2 * j + 1], f.y, acc);
+                    }
+                }
+                sv[t] = acc;
+                mx = fmaxf(mx, acc);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        __syncthreads();   // s_red is free (previous row / previous use)
+        if (lane == 0) s_red[warp] = mx;
+        __syncthreads();
+        mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+        // p = exp2((s - max) * sc); partial sum and partial output of this thread's keys
+        float sum = 0.f;
+        float of[64];
+#pragma unroll
+        for (int c = 0; c < 64; ++c) of[c] = 0.f;
+#pragma unroll
+        for (int t = 0; t < 5; ++t) {
+            const int key = threadIdx.x + 128 * t;
+            if (key < S) {
+                // the tensor path rounds P to bf16 before P V: do the same so both paths agree to rounding
+                const float e = __bfloat162float(__float2bfloat16_rn(ex2_fast((sv[t] - mx) * sc)));
+                sum += ex2_fast((sv[t] - mx) * sc);
+                const __nv_bfloat16* v = base + static_cast<int64_t>(key) * (3 * d) + 2 * d;
+#pragma unroll
+                for (int c = 0; c < 64; c += 8) {
+                    const uint4 u = __ldg(reinterpret_cast<const uint4*>(v + c));
+                    const uint32_t wv[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 f = unpack_bf16(wv[j]);
+                        of[c + 2 * j] = fmaf(e, f.x, of[c + 2 * j]);
+                        of[c + 2 * j + 1] = fmaf(e, f.y, of[c + 2 * j + 1]);
+                    }
+                }
+            }
+        }
+        // reduce the 65 values (64 outputs + the sum) over the warp, then over the 4 warps through shared memory
+#pragma unroll
+        for (int c = 0; c < 64; ++c)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) of[c] += __shfl_xor_sync(0xffffffffu, of[c], o);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        __syncthreads();
+        if (lane == 0) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) s_red[warp * 66 + c] = of[c];
+            s_red[warp * 66 + 64] = sum;
+        }
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            const int c = threadIdx.x;
+            const float l = s_red[64] + s_red[66 + 64] + s_red[132 + 64] + s_red[198 + 64];
+            const float v = s_red[c] + s_red[66 + c] + s_red[132 + c] + s_red[198 + c];
+            p.out[(static_cast<int64_t>(b) * S + row) * d + h * 64 + c] = __float2bfloat16_rn(v / l);
+            if (c == 0 && p.lse != nullptr) p.lse[(static_cast<int64_t>(b) * p.H + h) * S + row] = mx * sc + log2f(l);
+        }
+    }
+    __syncthreads();
+}
 constexpr int kLongSmem = kTile + 2 * kLongKvbMax * 128 + 3 * kTile + 1024;
 __global__ void __launch_bounds__(kAttnThreads)
 attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv,
@@ -314,6 +422,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_q, bar_k, bar_v, bar_mma;
     __shared__ uint32_t tmem_slot;
+    __shared__ float s_red[4 * 66];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + kTile;
@@ -341,7 +450,10 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 
     const int S = p.S, H = p.H, KVB = p.kvb;
     const int d = H * 64;
-    const int nqb = (S + 127) / 128;
+    // A handful of rows past the last full 128-row query block (ViT-L/14: 257 = 2 x 128 + 1) do not get a tensor-core
+    // block of their own -- it would cost as much as a full one -- but a SIMT pass by the CTA of the last full block.
+    const int tail = (!p.causal && (S & 127) <= p.tail_max) ? (S & 127) : 0;
+    const int nqb = tail ? S / 128 : (S + 127) / 128;
     const uint32_t kv_bytes = static_cast<uint32_t>(KVB) * 128u;
     const uint32_t idesc_s = make_idesc_bf16(128, KVB, 0, 0);
     const uint32_t idesc_o = make_idesc_bf16(128, 64, 0, 1);
@@ -477,6 +589,7 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
             }
             if (p.lse != nullptr) p.lse[(static_cast<int64_t>(b) * H + h) * S + row] = m * sc + log2f(l);
         }
+        if (tail && qb == nqb - 1) long_tail_rows(p, b, h, nqb * 128, tail, s_red);
     }
     if (warp == 0) {
         __syncwarp();
@@ -1055,6 +1168,13 @@ extern "C" int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, 
         if ((rc = make_tmap_bf16_2d(ctx, &tmkv, qkv, 3 * H * 64, B * S, 3 * H * 64, 64, static_cast<uint32_t>(kvb)))) return rc;
         AttnParams pl{};
         pl.kvb = kvb;
+        pl.qkv = static_cast<const __nv_bfloat16*>(qkv);
+        static const int tail_max = [] {
+            const char* e = getenv("B200CLIP_LONG_TAIL");   // tuning: 0 disables the SIMT tail
+            const int v = e ? atoi(e) : kLongTailMax;
+            return v < 0 ? 0 : (v > kLongTailMax ? kLongTailMax : v);
+        }();
+        pl.tail_max = causal ? 0 : tail_max;
         pl.out = static_cast<__nv_bfloat16*>(out);
         pl.lse = lse;
         pl.B = static_cast<int>(B);
@@ -1062,7 +1182,7 @@ extern "C" int b200clip_attn_fwd(b200clip_ctx* ctx, const void* qkv, void* out, 
         pl.H = static_cast<int>(H);
         pl.causal = causal ? 1 : 0;
         pl.npad = 128;
-        const int64_t work_l = B * H * ((S + 127) / 128);
+        const int64_t work_l = B * H * (((S & 127) <= pl.tail_max && (S & 127)) ? S / 128 : (S + 127) / 128);
         B200_CHECK_ARG(work_l < (1ll << 31), "attention: extent too large");
         const int grid_l = static_cast<int>(work_l < ctx->num_sms * 2 ? work_l : ctx->num_sms * 2);
         attn_fwd_long_kernel<<<grid_l, kAttnThreads, kLongSmem, static_cast<cudaStream_t>(stream)>>>(tml, tmkv, pl);

@@ -34,6 +34,9 @@ from . import towers as T
 
 bf16, f32 = torch.bfloat16, torch.float32
 
+import os as _os
+FEATURE_GATHER_BY_ALLREDUCE = _os.environ.get("B200CLIP_FEATURE_GATHER", "allreduce") != "allgather"
+
 
 def _world(group):
     if dist.is_available() and dist.is_initialized():
@@ -63,7 +66,17 @@ class _LossState:
         self.img_n, self.inv_i = O.l2norm_fwd(img_f.contiguous())
         self.txt_n, self.inv_t = O.l2norm_fwd(txt_f.contiguous())
         if world > 1:
-            both = _all_gather_rows(torch.cat([self.img_n, self.txt_n], dim=1), group, world)  # [Bg, 2E]
+            if FEATURE_GATHER_BY_ALLREDUCE:
+                # The one data-path collective of the forward sits on the critical path between the towers and the
+                # loss, and it is tiny (Bl x 2E fp32 per rank): a ring all-gather pays one hop per rank (147 us at 8
+                # GPUs in profiles/r02_timeline_n8.txt).  Summing zero-padded copies gives the same matrix bit for
+                # bit (x + 0 is exact) through NCCL's latency-optimised all-reduce.
+                both = torch.zeros((self.Bg, 2 * E), device=img_f.device, dtype=f32)
+                both[self.row0:self.row0 + Bl, :E] = self.img_n
+                both[self.row0:self.row0 + Bl, E:] = self.txt_n
+                dist.all_reduce(both, group=group)
+            else:
+                both = _all_gather_rows(torch.cat([self.img_n, self.txt_n], dim=1), group, world)  # [Bg, 2E]
             self.img_all = both[:, :E].contiguous()
             self.txt_all = both[:, E:].contiguous()
         else:
