@@ -29,18 +29,28 @@ void set_error(const char* fmt, ...) {
 
 int make_tmap_bf16_2d(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1,
                       uint64_t pitch_elems, uint32_t box0, uint32_t box1) {
+    return make_tmap_bf16_2d_sw(ctx, out, ptr, dim0, dim1, pitch_elems, box0, box1, 128);
+}
+
+int make_tmap_bf16_2d_sw(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1,
+                         uint64_t pitch_elems, uint32_t box0, uint32_t box1, int swizzle_bytes) {
+    if (swizzle_bytes != 128 && swizzle_bytes != 64) {
+        set_error("tensor map: swizzle %d not supported", swizzle_bytes);
+        return B200CLIP_ERR_ARG;
+    }
     if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || (pitch_elems * 2) % 16 != 0) {
         set_error("tensor map: pointer %p / pitch %llu elements not 16-byte aligned", ptr,
                   (unsigned long long)pitch_elems);
         return B200CLIP_ERR_ARG;
     }
-    if (box0 * 2 > 128 || box1 > 256 || box0 == 0 || box1 == 0) {
+    if (box0 * 2 > static_cast<uint32_t>(swizzle_bytes) || box1 > 256 || box0 == 0 || box1 == 0) {
         set_error("tensor map: bad box %u x %u", box0, box1);
         return B200CLIP_ERR_ARG;
     }
     // cache lookup (one context is driven by one host thread at a time; entries are written whole before use)
     const uint64_t key[4] = {reinterpret_cast<uint64_t>(ptr), dim0, dim1,
-                             (pitch_elems << 20) | (static_cast<uint64_t>(box0) << 10) | box1};
+                             (pitch_elems << 20) | (static_cast<uint64_t>(box0) << 10) | box1 |
+                                 (static_cast<uint64_t>(swizzle_bytes == 64) << 63)};
     TmapCacheEntry* slot = nullptr;
     if (ctx->tmap_cache != nullptr) {
         uint64_t h = key[0] * 0x9E3779B97F4A7C15ull ^ key[1] * 0xC2B2AE3D27D4EB4Full ^ key[2] * 0x165667B19E3779F9ull ^ key[3];
@@ -58,7 +68,8 @@ int make_tmap_bf16_2d(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint
     cuuint32_t box[2] = {box0, box1};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = ctx->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box,
-                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                   swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): dims %llu x %llu pitch %llu box %u x %u", (int)r,

@@ -600,26 +600,29 @@ attn_fwd_long_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_cons
 // ------------------------------------------------------------------------------------------------
 // Backward.  With the forward's row log-sum-exp and D = rowsum(dO o O) known up front there is no
 // row reduction left: ONE pass over (S, dP) produces P and dS.  Two threads share a row (they take
-// different 16-column chunks), 8 warps per CTA, 2 CTAs per SM.
+// different 16-column chunks), 8 warps per CTA, 2 CTAs per SM (256 TMEM columns each).
+// All five input tiles of a work item (Q, dO, K, V and the forward's O) arrive by TMA.  With only two CTAs
+// per SM there is little occupancy to hide memory latency behind, so sequences <= 64 (the vision tower:
+// 8 KB tiles) keep TWO input buffers: the tiles of item i+1 are requested at the top of item i and have a
+// whole item to land.  Longer sequences (S = 77: 10 KB tiles, P / dS in two atoms) would not fit two CTAs
+// that way; they keep one buffer and refill it as soon as the second MMA batch has retired.
 template <bool BIG, bool VARLEN = false>
-__global__ void __launch_bounds__(kAttnBwdThreads)
+__global__ void __launch_bounds__(kAttnBwdThreads, 2)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                const AttnParams p) {
+                const __grid_constant__ CUtensorMap tm_o, const AttnParams p) {
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_load, bar_mma;
+    constexpr int NBUF = BIG ? 1 : 2;
+    __shared__ uint64_t bar_load[NBUF], bar_mma;
     __shared__ uint32_t tmem_slot;
     __shared__ float s_D[2][128];  // the two column-half partial sums of D = rowsum(dO o O) per row
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int S = p.S, H = p.H, npad = p.npad;
     const int TB = npad * 128;
     constexpr int kAtoms = BIG ? 2 : 1;
-    // order [P | dS | Q | dO | K | V]: 128-row A-operand reads (dS, Q, dO) spill into the next tile only
+    // order [P | dS | NBUF x (Q | dO | K | V | O)]: 128-row A-operand reads (dS, Q, dO) spill into the following tiles only
     uint8_t* sP = smem;
     uint8_t* sdS = sP + kAtoms * TB;
-    uint8_t* sQ = sdS + kAtoms * TB;
-    uint8_t* sdO = sQ + TB;
-    uint8_t* sK = sdO + TB;
-    uint8_t* sV = sK + TB;
+    uint8_t* sIn = sdS + kAtoms * TB;
     constexpr int kTmemCols = 256;
     // TMEM columns: [0,128) S, later dV [0,64) + dK [64,128);  [128,256) dP, later dQ [128,192)
 
@@ -628,11 +631,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int half = warp >> 2;            // which share of the columns / output chunks it takes
     const bool warp_live = (warp & 3) * 32 < npad;  // all-padding warps only take part in the barriers
 
-    zero_smem(smem, (4 + 2 * kAtoms) * TB);
+    zero_smem(smem, (5 * NBUF + 2 * kAtoms) * TB);
     if (threadIdx.x == 0) {
         prefetch_tmap(&tm_qkv);
         prefetch_tmap(&tm_do);
-        mbar_init(&bar_load, 1);
+        prefetch_tmap(&tm_o);
+#pragma unroll
+        for (int i = 0; i < NBUF; ++i) mbar_init(&bar_load[i], 1);
         mbar_init(&bar_mma, 1);
         fence_barrier_init();
     }
@@ -645,7 +650,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const uint32_t trow = tmem + (static_cast<uint32_t>((warp & 3) * 32) << 16);
 
     const int d = H * 64;
-    const uint32_t load_bytes = 4u * S * 128u;
+    const uint32_t load_bytes = 5u * S * 128u;
     const uint32_t idesc_s = make_idesc_bf16(128, npad, 0, 0);    // S = Q K^T, dP = dO V^T
     const uint32_t idesc_tn = make_idesc_bf16(128, 64, 1, 1);     // dV = P^T dO, dK = dS^T Q
     const uint32_t idesc_nn = make_idesc_bf16(128, 64, 0, 1);     // dQ = dS K
@@ -653,41 +658,54 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     const int num_work = p.B * H;
     constexpr bool varlen = VARLEN;
     int hw = 0;  // varlen: chunks of this warp pair's P / dS rows that may still hold a previous item's values
-    auto issue_loads = [&](int w) {
+    auto issue_loads = [&](int w, int buf) {
         const int b = w / H, h = w - b * H;
         int row0, len;
         item_rows<VARLEN>(p, b, row0, len);
-        mbar_arrive_expect_tx(&bar_load, load_bytes);
-        tma_load_2d(sQ, &tm_qkv, &bar_load, h * 64, row0);
-        tma_load_2d(sK, &tm_qkv, &bar_load, d + h * 64, row0);
-        tma_load_2d(sV, &tm_qkv, &bar_load, 2 * d + h * 64, row0);
-        tma_load_2d(sdO, &tm_do, &bar_load, h * 64, row0);
+        uint8_t* base = sIn + buf * 5 * TB;
+        mbar_arrive_expect_tx(&bar_load[buf], load_bytes);
+        tma_load_2d(base, &tm_qkv, &bar_load[buf], h * 64, row0);
+        tma_load_2d(base + TB, &tm_do, &bar_load[buf], h * 64, row0);
+        tma_load_2d(base + 2 * TB, &tm_qkv, &bar_load[buf], d + h * 64, row0);
+        tma_load_2d(base + 3 * TB, &tm_qkv, &bar_load[buf], 2 * d + h * 64, row0);
+        tma_load_2d(base + 4 * TB, &tm_o, &bar_load[buf], h * 64, row0);
+    };
+    // the forward's row log-sum-exp of work item w for this thread's row (0 for rows past the sample)
+    auto fetch_lse = [&](int w) -> float {
+        if (w >= num_work) return 0.f;
+        const int b = w / H, h = w - b * H;
+        int row0, len;
+        item_rows<VARLEN>(p, b, row0, len);
+        return r < len ? __ldg(p.lse + lse_index<VARLEN>(p, b, h, row0, r)) : 0.f;
     };
     griddep_launch_dependents();
     griddep_wait();  // the prologue above overlapped the previous kernel's tail; global memory from here on
-    if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < num_work) issue_loads(blockIdx.x);
+    if (threadIdx.x == 0 && static_cast<int>(blockIdx.x) < num_work) issue_loads(blockIdx.x, 0);
+    float m2_next = fetch_lse(blockIdx.x);
     zero_surplus_rows<VARLEN>(p);
     uint32_t it = 0;
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++it) {
         const int b = w / H, h = w - b * H;
         int row0, Si;
         item_rows<VARLEN>(p, b, row0, Si);
+        const int buf = NBUF == 2 ? static_cast<int>(it & 1u) : 0;
+        const uint32_t load_phase = NBUF == 2 ? ((it >> 1) & 1u) : (it & 1u);
+        uint8_t* sQ = sIn + buf * 5 * TB;
+        uint8_t* sdO = sQ + TB;
+        uint8_t* sK = sdO + TB;
+        uint8_t* sV = sK + TB;
+        uint8_t* sO = sV + TB;
+        // two buffers: the other one was last read by item it-1, which ended with a __syncthreads
+        if (NBUF == 2 && threadIdx.x == 0 && w + static_cast<int>(gridDim.x) < num_work)
+            issue_loads(w + gridDim.x, buf ^ 1);
         const bool live = r < Si;
         const int lim = row_limit(r, Si, p.causal);                                // attended columns of this row
         const int wchunks = (warp_limit((warp & 3) * 32, Si, p.causal) + 15) >> 4;  // 16-column chunks this warp pair visits
-        // row statistics from the forward, fetched while the tiles are in flight; the two threads of a
-        // row each take half of the 64 columns of D = rowsum(dO o O)
-        float m2 = 0.f;
-        uint4 ov[4];
-        if (live) {
-            m2 = p.lse[lse_index<VARLEN>(p, b, h, row0, r)];
-            const uint4* op =
-                reinterpret_cast<const uint4*>(p.o + static_cast<int64_t>(row0 + r) * d + h * 64) + half * 4;
-#pragma unroll
-            for (int c = 0; c < 4; ++c) ov[c] = __ldg(op + c);
-        }
+        // row statistic from the forward: fetched one item ahead, so its latency is never exposed
+        const float m2 = m2_next;
+        m2_next = fetch_lse(w + gridDim.x);
         if (threadIdx.x == 0) {
-            mbar_wait(&bar_load, it & 1u);
+            mbar_wait(&bar_load[buf], load_phase);
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -700,15 +718,16 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             umma_commit(&bar_mma);
         }
         if (warp_live) {
-            // D = rowsum(dO o O) while the tensor core works
-            mbar_wait(&bar_load, it & 1u);
+            // D = rowsum(dO o O) while the tensor core works; the two threads of a row each take half of the 64 columns
+            mbar_wait(&bar_load[buf], load_phase);
             float part = 0.f;
             if (live) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const int cc = half * 4 + c;
                     const uint4 dv = *reinterpret_cast<const uint4*>(sdO + r * 128 + ((cc ^ (r & 7)) << 4));
-                    const uint32_t a[4] = {dv.x, dv.y, dv.z, dv.w}, o4[4] = {ov[c].x, ov[c].y, ov[c].z, ov[c].w};
+                    const uint4 ov = *reinterpret_cast<const uint4*>(sO + r * 128 + ((cc ^ (r & 7)) << 4));
+                    const uint32_t a[4] = {dv.x, dv.y, dv.z, dv.w}, o4[4] = {ov.x, ov.y, ov.z, ov.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         const float2 x = unpack_bf16(a[j]), y = unpack_bf16(o4[j]);
@@ -799,8 +818,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         }
         if (warp_live) {
             mbar_wait(&bar_mma, 1u);
-            // every tile is free again: fetch the next work item under this one's epilogue
-            if (threadIdx.x == 0 && w + static_cast<int>(gridDim.x) < num_work) issue_loads(w + gridDim.x);
+            // one buffer: every tile is free again, fetch the next work item under this one's epilogue
+            if (NBUF == 1 && threadIdx.x == 0 && w + static_cast<int>(gridDim.x) < num_work) issue_loads(w + gridDim.x, 0);
             __syncwarp();
             tc_fence_after();
             // six 32-column output chunks per row: dQ (TMEM 128..191), dK (64..127), dV (0..63);
@@ -1092,9 +1111,10 @@ static int fwd_smem(bool big, int npad) {
     return (have > need ? have : need) + 1024;
 }
 static int bwd_smem(bool big, int npad) {
-    const int tb = npad * 128, atoms = big ? 2 : 1;
-    const int need = (2 * atoms + 1) * tb + kTile;  // dO starts after P, dS, Q and is read for 128 rows
-    const int have = (4 + 2 * atoms) * tb;
+    const int tb = npad * 128, atoms = big ? 2 : 1, nbuf = big ? 1 : 2;  // (NBUF of attn_bwd_kernel)
+    // the last buffer's dO starts after P, dS, the earlier buffers and its own Q, and is read for 128 rows
+    const int need = (2 * atoms + 5 * (nbuf - 1) + 1) * tb + kTile;
+    const int have = (5 * nbuf + 2 * atoms) * tb;
     return (have > need ? have : need) + 1024;
 }
 
@@ -1259,10 +1279,12 @@ extern "C" int b200clip_attn_bwd_varlen(b200clip_ctx* ctx, const void* qkv, cons
                    "attn_bwd_varlen: needs out, lse, cu, total_rows and S_max <= 128");
     B200_CHECK_ARG(dqkv && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                    "attention: dqkv / out null or misaligned");
-    CUtensorMap tm, tmdo;
+    CUtensorMap tm, tmdo, tmo;
     if ((rc = make_tmap_bf16_2d(ctx, &tm, qkv, 3 * H * 64, total_rows, 3 * H * 64, 64, static_cast<uint32_t>(S_max))))
         return rc;
     if ((rc = make_tmap_bf16_2d(ctx, &tmdo, dout, H * 64, total_rows, H * 64, 64, static_cast<uint32_t>(S_max))))
+        return rc;
+    if ((rc = make_tmap_bf16_2d(ctx, &tmo, out, H * 64, total_rows, H * 64, 64, static_cast<uint32_t>(S_max))))
         return rc;
     AttnParams p{};
     p.o = static_cast<const __nv_bfloat16*>(out);
@@ -1283,9 +1305,9 @@ extern "C" int b200clip_attn_bwd_varlen(b200clip_ctx* ctx, const void* qkv, cons
     const int grid = static_cast<int>(work < ctx->num_sms * per_sm ? work : ctx->num_sms * per_sm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (big)
-        B200_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true, true>, dim3(grid), dim3(kAttnBwdThreads), smem, st, tm, tmdo, p));
+        B200_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true, true>, dim3(grid), dim3(kAttnBwdThreads), smem, st, tm, tmdo, tmo, p));
     else
-        B200_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false, true>, dim3(grid), dim3(kAttnBwdThreads), smem, st, tm, tmdo, p));
+        B200_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false, true>, dim3(grid), dim3(kAttnBwdThreads), smem, st, tm, tmdo, tmo, p));
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -1329,9 +1351,10 @@ extern "C" int b200clip_attn_bwd(b200clip_ctx* ctx, const void* qkv, const void*
     }
     B200_CHECK_ARG(dqkv && (reinterpret_cast<uintptr_t>(dqkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
                    "attention: dqkv / out null or misaligned");
-    CUtensorMap tm, tmdo;
+    CUtensorMap tm, tmdo, tmo;
     if ((rc = make_tmap_bf16_2d(ctx, &tm, qkv, 3 * H * 64, B * S, 3 * H * 64, 64, static_cast<uint32_t>(S)))) return rc;
     if ((rc = make_tmap_bf16_2d(ctx, &tmdo, dout, H * 64, B * S, H * 64, 64, static_cast<uint32_t>(S)))) return rc;
+    if ((rc = make_tmap_bf16_2d(ctx, &tmo, out, H * 64, B * S, H * 64, 64, static_cast<uint32_t>(S)))) return rc;
     AttnParams p{};
     p.o = static_cast<const __nv_bfloat16*>(out);
     p.lse = const_cast<float*>(lse);
@@ -1348,9 +1371,9 @@ extern "C" int b200clip_attn_bwd(b200clip_ctx* ctx, const void* qkv, const void*
     const int grid = static_cast<int>(work < ctx->num_sms * per_sm ? work : ctx->num_sms * per_sm);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (big)
-        B200_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, dim3(grid), dim3(kAttnBwdThreads), smem, st, tm, tmdo, p));
+        B200_CHECK_CUDA(launch_pdl(attn_bwd_kernel<true>, dim3(grid), dim3(kAttnBwdThreads), smem, st, tm, tmdo, tmo, p));
     else
-        B200_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, dim3(grid), dim3(kAttnBwdThreads), smem, st, tm, tmdo, p));
+        B200_CHECK_CUDA(launch_pdl(attn_bwd_kernel<false>, dim3(grid), dim3(kAttnBwdThreads), smem, st, tm, tmdo, tmo, p));
     B200_LAUNCH_CHECK();
     return 0;
 }

@@ -95,6 +95,7 @@ struct GemmParams {
     int num_m_tiles, num_n_tiles;
     int split_k, kb_total, kb_per_split;
     int out_f32, atomic_out, epilogue;
+    int tma_store;  // EPI_QUICKGELU only: row-layout epilogue, outputs leave through TMA stores (tmC / tmP are valid)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -224,7 +225,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
     __syncwarp();
     if (taddr_next == 0u && lane == 0) {
         if constexpr (PAIR)
-            mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), 0));
+            mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), cluster_ctarank() & ~1u));
         else
             mbar_arrive(release_bar);
     }
@@ -245,7 +246,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
 #if B200_EPI_EARLY_RELEASE
     else if (lane == 0) {  // every lane's loads completed before the __syncwarp above
         if constexpr (PAIR)
-            mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), 0));  // the leader's barrier
+            mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), cluster_ctarank() & ~1u));  // the leader's barrier
         else
             mbar_arrive(release_bar);
     }
@@ -325,7 +326,7 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
 #if !B200_EPI_EARLY_RELEASE
     if (taddr_next == 0u && lane == 0) {
         if constexpr (PAIR)
-            mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), 0));
+            mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), cluster_ctarank() & ~1u));
         else
             mbar_arrive(release_bar);
     }
@@ -365,7 +366,7 @@ __device__ __forceinline__ void drain_tile(const GemmParams& p, uint64_t* full_b
         tc_fence_before();
         if (lane == 0) {
             if constexpr (PAIR)
-                mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), 0));
+                mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), cluster_ctarank() & ~1u));
             else
                 mbar_arrive(release_bar);
         }
@@ -401,21 +402,111 @@ __device__ __forceinline__ void drain_tile(const GemmParams& p, uint64_t* full_b
 #undef B200_NEXT
 }
 
+// ------------------------------------------------------------------------------------------------
+// Row-layout epilogue with TMA stores, for the fattest epilogue of the model: c_fc forward = bias + QuickGELU with
+// TWO bf16 outputs (activation and saved pre-activation).  The coalesced-layout path above spends 12.2 warp
+// instructions per output element on this flavour (ncu source page, profiles/r02_gemm_fc_fwd_epilogue_sass.md): 6 of
+// maths, the rest on the fp32 transpose through shared memory, per-row pointer / predicate arithmetic and 8-byte
+// predicated stores -- and a tile takes 12.6 k cycles of epilogue against 6.1 k cycles of MMAs.  Here every thread
+// keeps its accumulator ROW (the TMEM layout), does the maths in place, writes bf16 rows into a 64-byte-swizzled
+// 32 x 32 staging tile (conflict free: chunk ^ ((row >> 1) & 3)) and one lane hands the tile to the TMA unit, which
+// coalesces and clips it at the matrix edge: no transposition, no address arithmetic, no predicates, no LSU stores.
+// The bias of a block is the same 32 values for every lane: four warp-uniform 16-byte loads.
+template <bool PRE, bool PAIR>
+__device__ __forceinline__ void drain_tile_rows_qgelu(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmP,
+                                                      uint64_t* full_bar, uint32_t phase, uint64_t* release_bar,
+                                                      uint32_t taddr, int m_base, int n_base, int nblk, float scale,
+                                                      uint8_t* stg, int lane) {
+    mbar_wait(full_bar, phase);
+    __syncwarp();
+    tc_fence_after();
+    const uint32_t sw = static_cast<uint32_t>((lane >> 1) & 3);
+    uint8_t* row_g = stg + lane * 64;
+    uint8_t* row_p = row_g + 2048;
+#pragma unroll 1
+    for (int j = 0; j < nblk; ++j) {
+        const int cb = n_base + j * 32;
+        uint32_t acc[32];
+        tmem_ld_32x32(taddr + j * 32, acc);
+        uint4 bq[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            bq[c] = make_uint4(0u, 0u, 0u, 0u);
+            if (p.bias != nullptr && cb + 8 * c + 8 <= p.N)  // warp-uniform
+                bq[c] = __ldg(reinterpret_cast<const uint4*>(p.bias + cb) + c);
+        }
+        tmem_ld_wait();
+        if (j + 1 == nblk) {  // the accumulator stage is drained: hand it back before the maths
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (PAIR)
+                    mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), cluster_ctarank() & ~1u));
+                else
+                    mbar_arrive(release_bar);
+            }
+        }
+        uint32_t pg[16];
+        [[maybe_unused]] uint32_t pp[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t bw[4] = {bq[c].x, bq[c].y, bq[c].z, bq[c].w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 bf = unpack_bf16(bw[k]);
+                const float x0 = fmaf(__uint_as_float(acc[8 * c + 2 * k]), scale, bf.x);
+                const float x1 = fmaf(__uint_as_float(acc[8 * c + 2 * k + 1]), scale, bf.y);
+                if constexpr (PRE) pp[4 * c + k] = pack_bf16(x0, x1);
+                pg[4 * c + k] = pack_bf16(qgelu_fast(x0), qgelu_fast(x1));
+            }
+        }
+        // the previous block's stores must have read the staging tile before it is overwritten
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint32_t off = (static_cast<uint32_t>(c) ^ sw) << 4;
+            *reinterpret_cast<uint4*>(row_g + off) = make_uint4(pg[4 * c], pg[4 * c + 1], pg[4 * c + 2], pg[4 * c + 3]);
+            if constexpr (PRE)
+                *reinterpret_cast<uint4*>(row_p + off) = make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tmC, stg, cb, m_base);
+            if constexpr (PRE) tma_store_2d(tmP, stg + 2048, cb, m_base);
+            tma_store_commit();
+        }
+    }
+    if (nblk <= 0) {  // nothing to drain (tile entirely past N): just hand the stage back
+        tc_fence_before();
+        if (lane == 0) {
+            if constexpr (PAIR)
+                mbar_arrive_cluster(mapa_shared(smem_u32(release_bar), cluster_ctarank() & ~1u));
+            else
+                mbar_arrive(release_bar);
+        }
+    }
+}
+
 // The whole persistent loop of one epilogue warp, specialised on the epilogue flavour.
-// PAIR = true: the CTA is one half of a cta_group::2 pair working on a 256-row tile; it owns rows
+// CL > 1: the CTA is one of CL CTAs of a cluster (cta_group::2 pairs) working on a CL x 128-row tile; it owns rows
 // [rank*128, rank*128+128) of the tile, iterates over the work list of its CLUSTER and releases the
 // accumulator stage on the LEADER CTA's barrier.
-template <int BN, int EPI, bool OUT_F32, bool ATOMIC, bool PAIR = false>
+template <int BN, int EPI, bool OUT_F32, bool ATOMIC, int CL = 1>
 __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem_base, uint64_t* tmem_full_bar,
-                                           uint64_t* tmem_empty_bar, uint8_t* stg, int warp, int lane, int num_work) {
+                                           uint64_t* tmem_empty_bar, uint8_t* stg, int warp, int lane, int num_work,
+                                           [[maybe_unused]] const CUtensorMap* tmC = nullptr,
+                                           [[maybe_unused]] const CUtensorMap* tmP = nullptr) {
     const int quad = warp & 3;         // TMEM lane quadrant this warp may access
     const int part = (warp - 2) >> 2;  // which share of the tile's columns this warp drains
     const float scale = (p.scale != nullptr) ? __ldg(p.scale) : 1.0f;
     int as = 0;
     uint32_t aphase = 0;
+    constexpr bool PAIR = CL > 1;  // CL = CTAs per cluster: 1, 2 (one cta_group::2 pair) or 4 (two pairs stacked along M)
     const int rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
-    const int w0 = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
-    const int wstep = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+    const int w0 = static_cast<int>(blockIdx.x) / CL;
+    const int wstep = static_cast<int>(gridDim.x) / CL;
     // The pre-activation operand of the QuickGELU' epilogue is streamed once with one block of look-ahead
     // (2 KB in flight per warp).  Each lane pulls its row of the NEXT tile's aux region into L2 one tile
     // ahead (plain prefetch.global.L2: -4 % on the two c_proj dgrad shapes).  Not for the fp32 residual
@@ -432,7 +523,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
         if constexpr (kHasAux && B200_EPI_AUX_PREFETCH) {
             if (wq < num_work) {
                 const int tq = wq / p.split_k;
-                const int row = (tq / p.num_n_tiles) * (PAIR ? 2 * BM : BM) + rank * BM + quad * 32 + lane;
+                const int row = (tq / p.num_n_tiles) * (CL * BM) + rank * BM + quad * 32 + lane;
                 const int nb = (tq % p.num_n_tiles) * BN + blk0 * 32;
                 const int ncol = min(nblk_half * 32, p.N - nb);  // N % 8 == 0: a multiple of 16 bytes either way
                 if (row < p.M && ncol > 0) {
@@ -449,7 +540,7 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
     for (int w = w0; w < num_work; w += wstep) {
         prefetch_aux(w + wstep);
         const int tile = w / p.split_k;
-        const int m_base = (tile / p.num_n_tiles) * (PAIR ? 2 * BM : BM) + rank * BM + quad * 32;
+        const int m_base = (tile / p.num_n_tiles) * (CL * BM) + rank * BM + quad * 32;
         const int n_base = (tile % p.num_n_tiles) * BN + blk0 * 32;
         int nblk = nblk_half;
         const int valid = (p.N - n_base + 31) >> 5;  // blocks with at least one real column (warp-uniform)
@@ -461,7 +552,14 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
     drain_tile<EPI, OUT_F32, ATOMIC, FULL, PRE, PAIR>(p, &tmem_full_bar[as], aphase, &tmem_empty_bar[as], taddr, m_base, \
                                                       n_base, nblk, scale, stg, lane)
         if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
-            if (p.preact != nullptr) {
+            if (p.tma_store) {  // kernel-uniform
+                if (p.preact != nullptr)
+                    drain_tile_rows_qgelu<true, PAIR>(p, tmC, tmP, &tmem_full_bar[as], aphase, &tmem_empty_bar[as], taddr,
+                                                      m_base, n_base, nblk, scale, stg, lane);
+                else
+                    drain_tile_rows_qgelu<false, PAIR>(p, tmC, tmP, &tmem_full_bar[as], aphase, &tmem_empty_bar[as], taddr,
+                                                       m_base, n_base, nblk, scale, stg, lane);
+            } else if (p.preact != nullptr) {
                 if (full) B200_DRAIN(true, true);
                 else B200_DRAIN(false, true);
             } else {
@@ -478,12 +576,17 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
             aphase ^= 1u;
         }
     }
+    if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
+        // bulk stores in flight read this CTA's shared memory and must be complete before the grid is
+        if (p.tma_store && lane == 0) tma_store_wait_all<0>();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const GemmParams p) {
     using Cfg = GemmCfg<BN>;
     constexpr int kStages = Cfg::kStages;
 
@@ -503,6 +606,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if (p.tma_store) {
+            prefetch_tmap(&tmC);
+            if (p.preact != nullptr) prefetch_tmap(&tmP);
+        }
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -613,6 +720,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         uint8_t* stg = smem + kStages * Cfg::kStageBytes + (warp - 2) * kEpiStageBytes;
 #define EPI_LOOP(E, F32, AT) \
     epilogue_loop<BN, E, F32, AT>(p, tmem_base, tmem_full_bar, tmem_empty_bar, stg, warp, lane, num_work)
+#define EPI_LOOP_TMA(E, F32, AT) \
+    epilogue_loop<BN, E, F32, AT>(p, tmem_base, tmem_full_bar, tmem_empty_bar, stg, warp, lane, num_work, &tmC, &tmP)
         if (p.out_f32) {
             if (p.atomic_out)
                 EPI_LOOP(B200CLIP_EPI_NONE, true, true);
@@ -622,13 +731,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 EPI_LOOP(B200CLIP_EPI_NONE, true, false);
         } else {
             switch (p.epilogue) {
-                case B200CLIP_EPI_QUICKGELU: EPI_LOOP(B200CLIP_EPI_QUICKGELU, false, false); break;
+                case B200CLIP_EPI_QUICKGELU: EPI_LOOP_TMA(B200CLIP_EPI_QUICKGELU, false, false); break;
                 case B200CLIP_EPI_RESIDUAL: EPI_LOOP(B200CLIP_EPI_RESIDUAL, false, false); break;
                 case B200CLIP_EPI_QUICKGELU_BWD: EPI_LOOP(B200CLIP_EPI_QUICKGELU_BWD, false, false); break;
                 default: EPI_LOOP(B200CLIP_EPI_NONE, false, false); break;
             }
         }
 #undef EPI_LOOP
+#undef EPI_LOOP_TMA
     }
 
     tc_fence_before();
@@ -653,9 +763,20 @@ constexpr int kStagesPairFit = (kSmemBudget - 1024 - kEpiWarps * kEpiStageBytes)
 constexpr int kStagesPair = kStagesPairFit < 6 ? kStagesPairFit : 6;
 constexpr int kSmemBytesPair = kStagesPair * kStageBytesPair + kEpiWarps * kEpiStageBytes + 1024;
 
-template <bool A_MN, bool B_MN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
-gemm_pair_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+// CL = 4 (gemm_quad_bf16_kernel): TWO pairs stacked along M share every B tile.  All these GEMMs run into the same
+// wall -- the L2 slices deliver ~6300 B / clock to the whole chip (B300_MICROARCH.md "LTS throughput cap"; 11.0-11.4
+// TB/s measured on every large shape of profiles/r01_gemm_shapes.txt once operand reads, aux reads and output
+// writes are added up) -- so the bytes a tile pulls through L2 per flop are what sets the speed.  In a cluster of
+// four, CTA (pair pp, half q) loads only a 64-column QUARTER of the B tile and the TMA unit multicasts it into
+// both pairs' CTAs of the same half: 16 KB of A + 8 KB of B per CTA and k-block instead of 16 + 16 (-25 % of the L2
+// reads).  Barrier protocol on top of the pair kernel's: a shared-memory slot of CTA X is also written by X's
+// M-neighbour (rank X ^ 2), so its empty barrier counts the MMA commits of BOTH pair leaders (multicast to all four
+// CTAs); the full barriers (in each pair leader) still count 2 producer arrivals and 64 KB of transactions, part of
+// which now come from the neighbour pair's multicasts.
+template <bool A_MN, bool B_MN, int CL>
+__device__ __forceinline__ void gemm_cluster_body(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmC,
+                                                  const CUtensorMap& tmP, const GemmParams& p) {
+    static_assert(CL == 2 || CL == 4, "cluster of one or two cta_group::2 pairs");
     constexpr int BN = 256;
     constexpr int kStages = kStagesPair;
     extern __shared__ uint8_t smem_raw[];
@@ -669,18 +790,25 @@ gemm_pair_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int rank = static_cast<int>(cluster_ctarank());
-    const bool leader = rank == 0;
+    const int q = rank & 1;               // which half of the pair (rows and B columns)
+    const int pp = rank >> 1;             // which pair of the cluster
+    const bool leader = q == 0;           // issues the pair's MMAs, owns its full / accumulator-empty barriers
+    const uint32_t leader_rank = static_cast<uint32_t>(rank & ~1);
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmA);
         prefetch_tmap(&tmB);
+        if (p.tma_store) {
+            prefetch_tmap(&tmC);
+            if (p.preact != nullptr) prefetch_tmap(&tmP);
+        }
         for (int s = 0; s < kStages; ++s) {
-            mbar_init(&full_bar[s], 2);   // leader: its own arrive.expect_tx + the peer producer's arrive
-            mbar_init(&empty_bar[s], 1);  // multicast commit of the leader's MMA warp
+            mbar_init(&full_bar[s], 2);        // leader: its own arrive.expect_tx + the peer producer's arrive
+            mbar_init(&empty_bar[s], CL / 2);  // multicast commit of every pair leader that reads data landing in this slot
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&tmem_full_bar[s], 1);
-            mbar_init(&tmem_empty_bar[s], 2 * kEpiWarps);  // leader: every epilogue warp of both CTAs
+            mbar_init(&tmem_empty_bar[s], 2 * kEpiWarps);  // leader: every epilogue warp of both CTAs of the pair
         }
         fence_barrier_init();
     }
@@ -692,19 +820,20 @@ gemm_pair_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     griddep_launch_dependents();
     griddep_wait();  // everything above overlapped the previous kernel's tail; global memory from here on
 
-    const int num_work = p.num_m_tiles * p.num_n_tiles * p.split_k;  // num_m_tiles counts 256-row tiles
-    const int w0 = static_cast<int>(blockIdx.x >> 1), wstep = static_cast<int>(gridDim.x >> 1);
+    const int num_work = p.num_m_tiles * p.num_n_tiles * p.split_k;  // num_m_tiles counts (CL x 128)-row tiles
+    const int w0 = static_cast<int>(blockIdx.x) / CL, wstep = static_cast<int>(gridDim.x) / CL;
 
     if (warp == 0) {
-        // ================== TMA producer (both CTAs: own A rows, own half of B) ==================
+        // ================== TMA producer (every CTA: own A rows, own share of B) ==================
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            const uint16_t mc_mask = static_cast<uint16_t>(0x5u << q);  // CTAs (0, q) and (1, q)
             for (int w = w0; w < num_work; w += wstep) {
                 const int split = w % p.split_k;
                 const int tile = w / p.split_k;
-                const int m0 = (tile / p.num_n_tiles) * (2 * BM) + rank * BM;
-                const int n0 = (tile % p.num_n_tiles) * BN + rank * (BN / 2);
+                const int m0 = (tile / p.num_n_tiles) * (CL * BM) + rank * BM;
+                const int n0 = (tile % p.num_n_tiles) * BN + q * (BN / 2);
                 const int kb0 = split * p.kb_per_split;
                 const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
                 for (int kb = kb0; kb < kb1; ++kb) {
@@ -712,7 +841,7 @@ gemm_pair_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                     if (leader)
                         mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytesPair);
                     else
-                        mbar_arrive_cluster(mapa_shared(smem_u32(&full_bar[stage]), 0));
+                        mbar_arrive_cluster(mapa_shared(smem_u32(&full_bar[stage]), leader_rank));
                     uint8_t* sA = smem + stage * kStageBytesPair;
                     uint8_t* sB = sA + kStageBytesA;
                     if constexpr (!A_MN) {
@@ -722,12 +851,20 @@ gemm_pair_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                         for (int j = 0; j < 2; ++j)
                             tma_load_2d_2sm(sA + j * (BK * 128), &tmA, &full_bar[stage], m0 + 64 * j, kb * BK);
                     }
-                    if constexpr (!B_MN) {
-                        tma_load_2d_2sm(sB, &tmB, &full_bar[stage], kb * BK, n0);
-                    } else {
+                    if constexpr (CL == 2) {
+                        if constexpr (!B_MN) {
+                            tma_load_2d_2sm(sB, &tmB, &full_bar[stage], kb * BK, n0);
+                        } else {
 #pragma unroll
-                        for (int j = 0; j < 2; ++j)
-                            tma_load_2d_2sm(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
+                            for (int j = 0; j < 2; ++j)
+                                tma_load_2d_2sm(sB + j * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * j, kb * BK);
+                        }
+                    } else {
+                        // this CTA's 64-column quarter of the B tile, delivered to both pairs (8 KB at the same offset)
+                        if constexpr (!B_MN)
+                            tma_load_2d_2sm_mc(sB + pp * (BK * 128), &tmB, &full_bar[stage], kb * BK, n0 + 64 * pp, mc_mask);
+                        else
+                            tma_load_2d_2sm_mc(sB + pp * (BK * 128), &tmB, &full_bar[stage], n0 + 64 * pp, kb * BK, mc_mask);
                     }
                     if (++stage == kStages) {
                         stage = 0;
@@ -737,9 +874,11 @@ gemm_pair_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
         }
     } else if (warp == 1) {
-        // ================== MMA issuer (leader CTA only) ==================
+        // ================== MMA issuer (pair leaders only) ==================
         if (lane == 0 && leader) {
             constexpr uint32_t idesc = make_idesc_bf16(2 * BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
+            constexpr uint16_t all_mask = static_cast<uint16_t>((1u << CL) - 1u);
+            const uint16_t pair_mask = static_cast<uint16_t>(3u << (2 * pp));
             int stage = 0;
             uint32_t phase = 0;
             int as = 0;
@@ -764,13 +903,13 @@ gemm_pair_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                                                  : make_smem_desc_sw128(sB + k * (UMMA_K * 2), 16, 1024);
                         umma_bf16_2sm(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     }
-                    umma_commit_2sm(&empty_bar[stage], 3);  // frees this slot in BOTH CTAs
+                    umma_commit_2sm(&empty_bar[stage], all_mask);  // this pair is done with the slot, in EVERY CTA of the cluster
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                umma_commit_2sm(&tmem_full_bar[as], 3);  // accumulators complete -> both epilogues
+                umma_commit_2sm(&tmem_full_bar[as], pair_mask);  // accumulators complete -> both epilogues of the pair
                 if (++as == 2) {
                     as = 0;
                     aphase ^= 1u;
@@ -778,10 +917,12 @@ gemm_pair_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
             }
         }
     } else {
-        // ================== epilogue warps (both CTAs drain their own 128 rows) ==================
+        // ================== epilogue warps (every CTA drains its own 128 rows) ==================
         uint8_t* stg = smem + kStages * kStageBytesPair + (warp - 2) * kEpiStageBytes;
 #define EPI_LOOP(E, F32, AT) \
-    epilogue_loop<BN, E, F32, AT, true>(p, tmem_base, tmem_full_bar, tmem_empty_bar, stg, warp, lane, num_work)
+    epilogue_loop<BN, E, F32, AT, CL>(p, tmem_base, tmem_full_bar, tmem_empty_bar, stg, warp, lane, num_work)
+#define EPI_LOOP_TMA(E, F32, AT) \
+    epilogue_loop<BN, E, F32, AT, CL>(p, tmem_base, tmem_full_bar, tmem_empty_bar, stg, warp, lane, num_work, &tmC, &tmP)
         if (p.out_f32) {
             if (p.atomic_out)
                 EPI_LOOP(B200CLIP_EPI_NONE, true, true);
@@ -791,21 +932,36 @@ gemm_pair_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
                 EPI_LOOP(B200CLIP_EPI_NONE, true, false);
         } else {
             switch (p.epilogue) {
-                case B200CLIP_EPI_QUICKGELU: EPI_LOOP(B200CLIP_EPI_QUICKGELU, false, false); break;
+                case B200CLIP_EPI_QUICKGELU: EPI_LOOP_TMA(B200CLIP_EPI_QUICKGELU, false, false); break;
                 case B200CLIP_EPI_RESIDUAL: EPI_LOOP(B200CLIP_EPI_RESIDUAL, false, false); break;
                 case B200CLIP_EPI_QUICKGELU_BWD: EPI_LOOP(B200CLIP_EPI_QUICKGELU_BWD, false, false); break;
                 default: EPI_LOOP(B200CLIP_EPI_NONE, false, false); break;
             }
         }
 #undef EPI_LOOP
+#undef EPI_LOOP_TMA
     }
 
     tc_fence_before();
-    cluster_sync_all();  // the peer's shared memory / TMEM must stay alive until the leader's MMAs are done
+    cluster_sync_all();  // peers' shared memory / TMEM must stay alive until every pair's MMAs and multicasts are done
     if (warp == 1) {
         __syncwarp();
         tmem_dealloc_2sm(tmem_base, 512);
     }
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_pair_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const GemmParams p) {
+    gemm_cluster_body<A_MN, B_MN, 2>(tmA, tmB, tmC, tmP, p);
+}
+
+template <bool A_MN, bool B_MN>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_quad_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmP, const GemmParams p) {
+    gemm_cluster_body<A_MN, B_MN, 4>(tmA, tmB, tmC, tmP, p);
 }
 
 template <bool A_MN, bool B_MN>
@@ -817,6 +973,41 @@ static int set_attr_pair() {
         return B200CLIP_ERR_CUDA;
     }
     return 0;
+}
+
+template <bool A_MN, bool B_MN>
+static int set_attr_quad() {
+    cudaError_t e = cudaFuncSetAttribute(gemm_quad_bf16_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         kSmemBytesPair);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(gemm quad): %s", cudaGetErrorString(e));
+        return B200CLIP_ERR_CUDA;
+    }
+    return 0;
+}
+
+// Output tensor maps of the TMA-store epilogue (p.tma_store): 32 x 32 bf16 boxes, 64-byte swizzle, clipped at M x N.
+static int make_store_tmaps(b200clip_ctx* ctx, const GemmParams& p, CUtensorMap* tmC, CUtensorMap* tmP) {
+    if (!p.tma_store) return 0;
+    int rc = make_tmap_bf16_2d_sw(ctx, tmC, p.C, p.N, p.M, p.ldc, 32, 32, 64);
+    if (rc == 0 && p.preact != nullptr) rc = make_tmap_bf16_2d_sw(ctx, tmP, p.preact, p.N, p.M, p.ldc, 32, 32, 64);
+    return rc;
+}
+
+// Persistent grid size for `work` items on `units` SMs (or CTA pairs).  The makespan is ceil(work / units)
+// waves whichever way the items are dealt, so the SMALLEST grid that still finishes in that many waves would
+// leave SMs to the kernels of the other tower's stream (two-stream step, section 5 of DESIGN.md) instead of
+// idling them through this kernel's partial last wave.  Measured at 128 pairs / GPU: 8.330 ms per step with it,
+// 8.285 ms without -- no gain, so it is opt-in (B200CLIP_MIN_GRID=1) and the default grid is `units`.
+static int persistent_grid(int64_t work, int units) {
+    static const bool min_grid = [] {
+        const char* e = getenv("B200CLIP_MIN_GRID");
+        return e && atoi(e) != 0;
+    }();
+    if (work <= units) return static_cast<int>(work);
+    if (!min_grid) return units;
+    const int64_t waves = ceil_div(work, static_cast<int64_t>(units));
+    return static_cast<int>(ceil_div(work, waves));
 }
 
 template <bool A_MN, bool B_MN>
@@ -834,12 +1025,42 @@ static int launch_pair(b200clip_ctx* ctx, const void* A, int64_t lda, const void
     else
         rc = make_tmap_bf16_2d(ctx, &tmB, B, p.N, p.K, ldb, 64, BK);
     if (rc) return rc;
+    CUtensorMap tmC{}, tmP{};
+    if ((rc = make_store_tmaps(ctx, p, &tmC, &tmP))) return rc;
     p.num_m_tiles = static_cast<int>(ceil_div(p.M, 2 * BM));
     p.num_n_tiles = static_cast<int>(ceil_div(p.N, 256));
     const int64_t work = static_cast<int64_t>(p.num_m_tiles) * p.num_n_tiles * p.split_k;
-    const int clusters = static_cast<int>(work < ctx->num_sms / 2 ? work : ctx->num_sms / 2);
+    const int clusters = persistent_grid(work, ctx->num_sms / 2);
     B200_CHECK_CUDA(launch_pdl(gemm_pair_bf16_kernel<A_MN, B_MN>, dim3(2 * clusters), dim3(kGemmThreads),
-                               kSmemBytesPair, stream, tmA, tmB, p));
+                               kSmemBytesPair, stream, tmA, tmB, tmC, tmP, p));
+    B200_LAUNCH_CHECK();
+    return 0;
+}
+
+// two pairs per cluster, B multicast (gemm_quad_bf16_kernel): 512 x 256 tiles over ctx->max_quads clusters
+template <bool A_MN, bool B_MN>
+static int launch_quad(b200clip_ctx* ctx, const void* A, int64_t lda, const void* B, int64_t ldb, GemmParams& p,
+                       cudaStream_t stream) {
+    CUtensorMap tmA, tmB;
+    int rc;
+    if (!A_MN)
+        rc = make_tmap_bf16_2d(ctx, &tmA, A, p.K, p.M, lda, BK, BM);
+    else
+        rc = make_tmap_bf16_2d(ctx, &tmA, A, p.M, p.K, lda, 64, BK);
+    if (rc) return rc;
+    if (!B_MN)
+        rc = make_tmap_bf16_2d(ctx, &tmB, B, p.K, p.N, ldb, BK, 64);  // this CTA's quarter of the 256 columns
+    else
+        rc = make_tmap_bf16_2d(ctx, &tmB, B, p.N, p.K, ldb, 64, BK);
+    if (rc) return rc;
+    CUtensorMap tmC{}, tmP{};
+    if ((rc = make_store_tmaps(ctx, p, &tmC, &tmP))) return rc;
+    p.num_m_tiles = static_cast<int>(ceil_div(p.M, 4 * BM));
+    p.num_n_tiles = static_cast<int>(ceil_div(p.N, 256));
+    const int64_t work = static_cast<int64_t>(p.num_m_tiles) * p.num_n_tiles * p.split_k;
+    const int clusters = persistent_grid(work, ctx->max_quads);
+    B200_CHECK_CUDA(launch_pdl(gemm_quad_bf16_kernel<A_MN, B_MN>, dim3(4 * clusters), dim3(kGemmThreads),
+                               kSmemBytesPair, stream, tmA, tmB, tmC, tmP, p));
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -856,7 +1077,7 @@ static int set_attr() {
     return 0;
 }
 
-int init_gemm(b200clip_ctx*) {
+int init_gemm(b200clip_ctx* ctx) {
     int rc = 0;
     if ((rc = set_attr<256, false, false>())) return rc;
     if ((rc = set_attr<256, false, true>())) return rc;
@@ -876,6 +1097,23 @@ int init_gemm(b200clip_ctx*) {
     if ((rc = set_attr_pair<false, false>())) return rc;
     if ((rc = set_attr_pair<false, true>())) return rc;
     if ((rc = set_attr_pair<true, true>())) return rc;
+    if ((rc = set_attr_quad<false, false>())) return rc;
+    if ((rc = set_attr_quad<false, true>())) return rc;
+    if ((rc = set_attr_quad<true, true>())) return rc;
+    // how many 4-CTA clusters of the quad kernel the device can hold at once (GPCs whose SM count is not a
+    // multiple of four strand one pair each); 0 disables the kernel
+    ctx->max_quads = 0;
+    {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(4 * (ctx->num_sms / 4));
+        cfg.blockDim = dim3(kGemmThreads);
+        cfg.dynamicSmemBytes = kSmemBytesPair;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, gemm_quad_bf16_kernel<false, false>, &cfg) == cudaSuccess && n > 0)
+            ctx->max_quads = n < ctx->num_sms / 4 ? n : ctx->num_sms / 4;
+        else
+            (void)cudaGetLastError();
+    }
     return 0;
 }
 
@@ -894,12 +1132,14 @@ static int launch(b200clip_ctx* ctx, const void* A, int64_t lda, const void* B, 
     else
         rc = make_tmap_bf16_2d(ctx, &tmB, B, p.N, p.K, ldb, 64, BK);
     if (rc) return rc;
+    CUtensorMap tmC{}, tmP{};
+    if ((rc = make_store_tmaps(ctx, p, &tmC, &tmP))) return rc;
     p.num_m_tiles = static_cast<int>(ceil_div(p.M, BM));
     p.num_n_tiles = static_cast<int>(ceil_div(p.N, BN));
     const int64_t work = static_cast<int64_t>(p.num_m_tiles) * p.num_n_tiles * p.split_k;
-    const int grid = static_cast<int>(work < ctx->num_sms ? work : ctx->num_sms);
+    const int grid = persistent_grid(work, ctx->num_sms);
     B200_CHECK_CUDA(launch_pdl(gemm_bf16_kernel<BN, A_MN, B_MN>, dim3(grid), dim3(kGemmThreads),
-                               GemmCfg<BN>::kSmemBytes, stream, tmA, tmB, p));
+                               GemmCfg<BN>::kSmemBytes, stream, tmA, tmB, tmC, tmP, p));
     B200_LAUNCH_CHECK();
     return 0;
 }
@@ -979,6 +1219,13 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
     p.kb_total = static_cast<int>(ceil_div(K, BK));
     p.out_f32 = out_f32 ? 1 : 0;
     p.epilogue = epilogue;
+    // c_fc forward (bias + QuickGELU, activation + saved pre-activation): row-layout epilogue with TMA stores
+    // (B200CLIP_EPI_TMA=0: the coalesced-layout path with LSU stores, for A/B measurements)
+    static const bool epi_tma = [] {
+        const char* e = getenv("B200CLIP_EPI_TMA");
+        return !(e && atoi(e) == 0);
+    }();
+    p.tma_store = (epi_tma && epilogue == B200CLIP_EPI_QUICKGELU && !out_f32) ? 1 : 0;
 
     // CTA-pair kernel (256 x 256 tiles over 74 clusters) when the problem has enough such tiles;
     // B200CLIP_GEMM_PAIR=0 disables it (tuning / bisecting)
@@ -986,11 +1233,22 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
         const char* e = getenv("B200CLIP_GEMM_PAIR");
         return !(e && atoi(e) == 0);
     }();
+    // Two pairs per cluster with the B tile multicast (gemm_quad_bf16_kernel) is OFF by default: measured on the 24
+    // GEMM shapes of a ViT-B/32 layer at 1024 pairs it LOSES 3 % (2769 vs 2685 us per layer; fc wgrad 203 vs 173 us)
+    // although it pulls 25 % fewer operand bytes through L2 -- four CTAs that must all retire a slot before any of
+    // them refills it, and 36 clusters instead of 74.  B200CLIP_GEMM_QUAD=1 enables it (read per call: tests flip it).
+    const bool quad_enabled = [] {
+        const char* e = getenv("B200CLIP_GEMM_QUAD");
+        return e && atoi(e) != 0;
+    }();
     const int clusters = ctx->num_sms / 2;
     const int sms = ctx->num_sms;
     const int64_t m_tiles = ceil_div(M, BM);
     const int64_t tiles_pair = ceil_div(M, 2 * BM) * ceil_div(N, 256);
+    const int64_t tiles_quad = ceil_div(M, 4 * BM) * ceil_div(N, 256);
     const bool pair_ok = pair_enabled && N >= 256 && M >= 2 * BM;
+    const bool quad_ok = pair_ok && quad_enabled && ctx->max_quads > 0 && M >= 4 * BM;
+    bool use_quad = false;
     const bool amn = a_major == B200CLIP_MAJOR_MN, bmn = b_major == B200CLIP_MAJOR_MN;
     auto tiles_of = [&](int bn) { return m_tiles * ceil_div(N, bn); };
     // Tile shape.  Atomic (split-K / accumulating) fp32 outputs -- the weight gradients -- take the widest
@@ -1012,10 +1270,21 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
         while (bn > 96 && bn > N + 31) bn -= 32;
     } else if (atomic_like) {
         use_pair = pair_ok;
+        // weight gradients balance the machine through split-K, so the quad kernel only has to avoid padding M much
+        use_quad = quad_ok && (ceil_div(M, 4 * BM) * 4 * BM - M) * 10 <= M;
         bn = N >= 256 ? 256 : (N >= 192 ? 192 : 128);
     } else {
         double best = pair_ok ? 0.95 * static_cast<double>(ceil_div(tiles_pair, clusters)) : 1e30;
         use_pair = pair_ok;
+        // a 512 x 256 quad tile takes kQuadCost of a pair tile's time (its two pairs run side by side on 3/4 of the L2 reads)
+        static const double quad_cost = [] {
+            const char* e = getenv("B200CLIP_QUAD_COST");
+            return e ? atof(e) : 0.80;
+        }();
+        if (quad_ok) {
+            const double c = quad_cost * static_cast<double>(ceil_div(tiles_quad, ctx->max_quads));
+            if (c < best - 1e-9) best = c, use_quad = true;
+        }
         // (224 and 96 exist and are tested, but lost on every shape they were predicted to win at 128 pairs / GPU:
         // fc fwd 33.9 -> 37.0 us, proj dgrad 38.8 -> 41.1 us with 224; 160 gains ~4 % on the N = 768 shapes)
         static const int widths[] = {256, 192, 160, 128};
@@ -1023,11 +1292,12 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
             if (w > N + 31 && w != 96) continue;          // wider than the problem: the next width covers it
             if (amn && (w % 64)) continue;                // (A MN-major, i.e. weight gradients: 64-multiples only)
             const double c = (0.24 + 0.76 * w / 256.0) * static_cast<double>(ceil_div(tiles_of(w), sms));
-            if (c < best - 1e-9) best = c, use_pair = false, bn = w;
+            if (c < best - 1e-9) best = c, use_pair = false, use_quad = false, bn = w;
         }
     }
-    const int64_t tiles = use_pair ? tiles_pair : tiles_of(bn);
-    if (split_k <= 0) split_k = out_f32 ? choose_split_k(tiles, p.kb_total, use_pair ? clusters : ctx->num_sms) : 1;
+    const int64_t tiles = use_quad ? tiles_quad : (use_pair ? tiles_pair : tiles_of(bn));
+    if (split_k <= 0)
+        split_k = out_f32 ? choose_split_k(tiles, p.kb_total, use_quad ? ctx->max_quads : (use_pair ? clusters : ctx->num_sms)) : 1;
     if (split_k > p.kb_total) split_k = p.kb_total;
     p.kb_per_split = static_cast<int>(ceil_div(p.kb_total, split_k));
     split_k = static_cast<int>(ceil_div(p.kb_total, p.kb_per_split));  // no empty splits
@@ -1035,6 +1305,11 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
     p.atomic_out = (out_f32 && (split_k > 1 || accumulate)) ? 1 : 0;
 
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (use_quad) {
+        if (!amn && !bmn) return launch_quad<false, false>(ctx, A, lda, B, ldb, p, st);
+        if (!amn && bmn) return launch_quad<false, true>(ctx, A, lda, B, ldb, p, st);
+        return launch_quad<true, true>(ctx, A, lda, B, ldb, p, st);
+    }
     if (use_pair) {
         if (!amn && !bmn) return launch_pair<false, false>(ctx, A, lda, B, ldb, p, st);
         if (!amn && bmn) return launch_pair<false, true>(ctx, A, lda, B, ldb, p, st);

@@ -26,6 +26,7 @@ constexpr int kTmapCacheSize = 2048;
 struct b200clip_ctx {
     int device;
     int num_sms;
+    int max_quads;  // co-resident 4-CTA clusters of gemm_quad_bf16_kernel (0: kernel unavailable)
     PFN_encodeTiled encode_tiled;
     TmapCacheEntry* tmap_cache;   // kTmapCacheSize entries, owned
     uint64_t tmap_hits, tmap_misses;
@@ -96,6 +97,10 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // pitch in elements; box = (box0 <= 64, box1 <= 256).
 int make_tmap_bf16_2d(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1,
                       uint64_t pitch_elems, uint32_t box0, uint32_t box1);
+
+// the same with a 64-byte swizzle (box0 <= 32): the 32 x 32 bf16 staging tiles of the GEMM's TMA-store epilogue
+int make_tmap_bf16_2d_sw(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1,
+                         uint64_t pitch_elems, uint32_t box0, uint32_t box1, int swizzle_bytes);
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -39,11 +39,20 @@ GEMM_SHAPES = [
     (77, 136, 72), (3000, 768, 3072), (32, 512, 768), (6400, 3072, 768),
     (20000, 768, 512), (19999, 520, 200),   # CTA-pair (cta_group::2) kernel: >= 74 tiles of 256 x 256, ragged edges
     (6400, 768, 768), (9856, 512, 1536), (6390, 776, 520),   # 128 x 192 tiles (75-78 pair tiles = 2 waves otherwise)
+    # 4-CTA clusters (two pairs, B multicast): >= 8 tiles of 512 x 256 per cluster (operand ring and both TMEM stages
+    # wrap several times), K not a multiple of 64, rows that leave the second pair of the last tile empty
+    (51200, 768, 256), (40000 + 130, 1024, 328),
 ]
 
 
+@pytest.fixture
+def quad(monkeypatch):
+    """The 4-CTA-cluster GEMM (B multicast) is off by default (measured slower); the large shapes run with it on."""
+    monkeypatch.setenv("B200CLIP_GEMM_QUAD", "1")
+
+
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-def test_gemm_nt(ops, M, N, K):
+def test_gemm_nt(ops, quad, M, N, K):
     a, b = _rand((M, K), seed=1), _rand((N, K), seed=2)
     got = ops.gemm(a, b)
     ref = a.float() @ b.float().t()
@@ -51,7 +60,7 @@ def test_gemm_nt(ops, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
-def test_gemm_nn_dgrad(ops, M, N, K):
+def test_gemm_nn_dgrad(ops, quad, M, N, K):
     from construction_clip_b200 import lib as L
     a, b = _rand((M, K), seed=3), _rand((K, N), seed=4)   # B stored [K, N]  (MN-major)
     got = ops.gemm(a, b, b_major=L.MAJOR_MN)
@@ -60,8 +69,9 @@ def test_gemm_nn_dgrad(ops, M, N, K):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 256, 128), (768, 768, 6400), (2304, 768, 1600),
-                                   (512, 2048, 9856), (136, 72, 77 * 8)])
-def test_gemm_tn_wgrad(ops, M, N, K):
+                                   (512, 2048, 9856), (136, 72, 77 * 8),
+                                   (3072, 768, 6400), (1024, 512, 20000)])   # 4-CTA clusters (M a multiple of 512)
+def test_gemm_tn_wgrad(ops, quad, M, N, K):
     from construction_clip_b200 import lib as L
     a, b = _rand((K, M), seed=5), _rand((K, N), seed=6)   # both stored [K, *]  (MN-major)
     out = torch.zeros((M, N), device="cuda", dtype=f32)
@@ -110,8 +120,11 @@ def test_gemm_every_tile_width(ops, bn, monkeypatch):
     _close(ops.gemm(a2, w2), a2.float() @ w2.float().t(), 3e-2, 1e-2, f"tall bn={bn}")
 
 
-@pytest.mark.parametrize("M", [1000, 6400, 20000])   # 6400 rows -> 128 x 192 tiles, 20000 rows -> CTA-pair kernel
-def test_gemm_epilogues(ops, M):
+@pytest.mark.parametrize("M", [1000, 6400, 20000, -20000])   # 6400 rows -> 128 x 192 tiles, 20000 rows -> CTA-pair kernel
+def test_gemm_epilogues(ops, M, monkeypatch):
+    if M < 0:   # the same through the 4-CTA-cluster kernel (two pairs, B multicast)
+        monkeypatch.setenv("B200CLIP_GEMM_QUAD", "1")
+        M = -M
     from construction_clip_b200 import lib as L
     N, K = 768, 512
     a, w = _rand((M, K), seed=7), _rand((N, K), 0.05, seed=8)
@@ -125,6 +138,10 @@ def test_gemm_epilogues(ops, M):
     got = ops.gemm(a, w, bias=bias, epilogue=L.EPI_QUICKGELU, preact=pre)
     _close(pre, base, 3e-2, 1e-2, "preact")
     _close(got, base * torch.sigmoid(1.702 * base), 3e-2, 1e-2, "quickgelu")
+    _close(ops.gemm(a, w, bias=bias, epilogue=L.EPI_QUICKGELU), base * torch.sigmoid(1.702 * base), 3e-2, 1e-2,
+           "quickgelu without the pre-activation output (inference)")
+    nb = a.float() @ w.float().t()
+    _close(ops.gemm(a, w, epilogue=L.EPI_QUICKGELU), nb * torch.sigmoid(1.702 * nb), 3e-2, 1e-2, "quickgelu, no bias")
     _close(ops.gemm(a, w, bias=bias, epilogue=L.EPI_RESIDUAL, aux=aux), base + aux.float(), 3e-2, 1e-2, "residual")
     auxf = torch.randn(M, N, device="cuda")
     _close(ops.gemm(a, w, bias=bias, epilogue=L.EPI_RESIDUAL, aux=auxf, out_dtype=f32), base + auxf, 1e-3, 1e-3,
@@ -221,7 +238,10 @@ def _attn_ref(qkv, B, S, H, causal):
 
 
 @pytest.mark.parametrize("B,S,H,causal", [(2, 50, 12, False), (3, 77, 8, True), (1, 64, 2, False), (2, 16, 2, True),
-                                          (1, 128, 2, True), (40, 50, 12, False), (33, 77, 8, True), (2, 7, 1, True)])
+                                          (1, 128, 2, True), (40, 50, 12, False), (33, 77, 8, True), (2, 7, 1, True),
+                                          # >= 4 work items per persistent CTA: both input buffers of the backward in both
+                                          # mbarrier phases (S <= 64), refill of the single buffer (S > 64)
+                                          (128, 50, 12, False), (160, 77, 8, True), (300, 33, 5, True)])
 def test_attention_fwd_bwd(ops, B, S, H, causal):
     qkv = _rand((B * S, 3 * H * 64), 1.5, seed=S)
     out, lse = ops.attn_fwd(qkv, B, S, H, causal, want_lse=True)
@@ -235,7 +255,10 @@ def test_attention_fwd_bwd(ops, B, S, H, causal):
 
 
 @pytest.mark.parametrize("lens,S,H,causal", [([77, 5, 33, 64, 1, 76, 17], 77, 8, True), ([50, 3, 20], 50, 2, False),
-                                             ([9] * 40 + [70, 2, 31], 77, 8, True)])
+                                             ([9] * 40 + [70, 2, 31], 77, 8, True),
+                                             # double-buffered backward (S_max <= 64), ~4 work items per CTA
+                                             ([int(x) for x in np.random.RandomState(3).randint(1, 65, 300)], 64, 4, True),
+                                             ([int(x) for x in np.random.RandomState(4).randint(1, 51, 150)], 50, 8, False)])
 def test_attention_varlen(ops, lens, S, H, causal):
     """Packed rows: every sample attends inside its own cu[b] .. cu[b+1]-1 rows only."""
     B, d = len(lens), H * 64

@@ -9,6 +9,12 @@ for STAGE in "$@"; do
     T0=$(date +%s)
     case $STAGE in
         tests)        timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 > gpurun_out/${TAG}_tests.log 2>&1 ;;
+        attn)         timeout 600 python -m pytest tests -m gpu -q -x --timeout 300 -k "attention or attn" > gpurun_out/${TAG}_attn.log 2>&1 ; tail -5 gpurun_out/${TAG}_attn.log ;;
+        graph128_nomin) B200CLIP_MIN_GRID=0 timeout 400 python tools/graph_bench.py 128 > gpurun_out/${TAG}_graph128_nomin.txt 2>&1 ;;
+        gemmtests)    timeout 600 python -m pytest tests -m gpu -q -x --timeout 300 -k "gemm" > gpurun_out/${TAG}_gemmtests.log 2>&1 ; tail -5 gpurun_out/${TAG}_gemmtests.log ;;
+        micro_notma)  B200CLIP_EPI_TMA=0 timeout 300 python tools/ncu_micro.py --time --only=fc_fwd > gpurun_out/${TAG}_micro_notma.txt 2>&1 ;;
+        gemm_noquad)  B200CLIP_GEMM_QUAD=0 timeout 300 python tools/gemm_bench.py 1024 > gpurun_out/${TAG}_gemm1024_noquad.txt 2>&1 ;;
+        gemmquick)    timeout -s KILL 150 python -m pytest tests -m gpu -q -x --timeout 60 -k "gemm" > gpurun_out/${TAG}_gemmtests.log 2>&1 ; tail -5 gpurun_out/${TAG}_gemmtests.log ;;
         tests_all)    timeout 900 python -m pytest tests -m gpu -q --timeout 300 > gpurun_out/${TAG}_tests.log 2>&1 ;;
         bench)        timeout 600 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
         bench_nv)     B200CLIP_BENCH_VARIANTS=0 timeout 400 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err ;;
