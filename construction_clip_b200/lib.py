@@ -60,8 +60,16 @@ SIGNATURES = {
     "b200clip_check_im2col_f32": [_p, _p, _p, _l, _l, _l, _l, _p],
     "b200clip_adamw": [_p, _p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _l, _p, _p],
     "b200clip_adamw_g16": [_p, _p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _l, _p, _p],
+    "b200clip_peer_buffer_bytes": [_i, _l],
+    "b200clip_peer_alloc": [_p, _l, C.POINTER(_p), _p],
+    "b200clip_peer_open": [_p, _p, C.POINTER(_p)],
+    "b200clip_peer_close": [_p, _p],
+    "b200clip_peer_free": [_p, _p],
+    "b200clip_peer_allgather": [_p, _p, _i, _i, _l, _i, _p, _p, _p, _p],
+    "b200clip_peer_status": [_p, _p, _p],
 }
-_RESTYPES = {"b200clip_last_error": C.c_char_p, "b200clip_launch_count": C.c_uint64, "b200clip_clip_loss_workspace_bytes": C.c_int64}
+_RESTYPES = {"b200clip_last_error": C.c_char_p, "b200clip_launch_count": C.c_uint64, "b200clip_clip_loss_workspace_bytes": C.c_int64,
+             "b200clip_peer_buffer_bytes": C.c_int64}
 
 _lib = None
 _lock = threading.RLock()

@@ -35,7 +35,8 @@ from . import towers as T
 bf16, f32 = torch.bfloat16, torch.float32
 
 import os as _os
-FEATURE_GATHER_BY_ALLREDUCE = _os.environ.get("B200CLIP_FEATURE_GATHER", "allreduce") != "allgather"
+from . import peer as _peer
+FEATURE_GATHER_BY_ALLREDUCE = _os.environ.get("B200CLIP_FEATURE_GATHER", "peer") != "allgather"
 
 
 def _world(group):
@@ -65,12 +66,19 @@ class _LossState:
         self.ls = logit_scale.detach().to(f32).reshape(1).contiguous()
         self.img_n, self.inv_i = O.l2norm_fwd(img_f.contiguous())
         self.txt_n, self.inv_t = O.l2norm_fwd(txt_f.contiguous())
-        if world > 1:
+        # The two exchanges between the towers and the loss.  Default: the library's own peer-memory all-gather over
+        # NVLink (peer.py / csrc/peer.cu: one kernel per rank, flags + direct loads from every peer, results written
+        # straight into the layouts the loss kernels read); NCCL when the exchange is unavailable or switched off.
+        ex = _peer.get(group, img_f.device, 2 * Bl * E * 4) if world > 1 else None
+        if ex is not None:
+            self.img_all = torch.empty((self.Bg, E), device=img_f.device, dtype=f32)
+            self.txt_all = torch.empty((self.Bg, E), device=img_f.device, dtype=f32)
+            ex.allgather([self.img_n, self.txt_n], [self.img_all, self.txt_all])
+        elif world > 1:
             if FEATURE_GATHER_BY_ALLREDUCE:
-                # The one data-path collective of the forward sits on the critical path between the towers and the
-                # loss, and it is tiny (Bl x 2E fp32 per rank): a ring all-gather pays one hop per rank (147 us at 8
-                # GPUs in profiles/r02_timeline_n8.txt).  Summing zero-padded copies gives the same matrix bit for
-                # bit (x + 0 is exact) through NCCL's latency-optimised all-reduce.
+                # A ring all-gather of this tiny message pays one hop per rank (147 us at 8 GPUs in
+                # profiles/r02_timeline_n8.txt).  Summing zero-padded copies gives the same matrix bit for bit (x + 0
+                # is exact) through NCCL's latency-optimised all-reduce.
                 both = torch.zeros((self.Bg, 2 * E), device=img_f.device, dtype=f32)
                 both[self.row0:self.row0 + Bl, :E] = self.img_n
                 both[self.row0:self.row0 + Bl, E:] = self.txt_n
@@ -83,7 +91,15 @@ class _LossState:
             self.img_all, self.txt_all = self.img_n, self.txt_n
         self.ws = O.clip_loss_workspace(img_f.device, Bl, self.Bg, E)
         lse_i, lse_t, loss_sum, correct = O.clip_loss_fwd(self.img_all, self.txt_all, self.ls, self.row0, Bl, self.ws)
-        if world > 1:
+        if ex is not None:
+            self.lse_i_all = torch.empty(self.Bg, device=img_f.device, dtype=f32)
+            self.lse_t_all = torch.empty(self.Bg, device=img_f.device, dtype=f32)
+            stats_all = torch.empty((world, 4), device=img_f.device, dtype=f32)
+            stats = torch.cat([loss_sum, correct.to(f32), correct.to(f32)])   # 4 floats = one 16-byte unit
+            ex.allgather([lse_i, lse_t, stats], [self.lse_i_all, self.lse_t_all, stats_all])
+            stats = stats_all.sum(0)
+            loss_sum, self.correct = stats[:2], stats[2]
+        elif world > 1:
             lse = _all_gather_rows(torch.stack([lse_i, lse_t], dim=1), group, world)  # [Bg, 2]
             self.lse_i_all, self.lse_t_all = lse[:, 0].contiguous(), lse[:, 1].contiguous()
             stats = torch.cat([loss_sum, correct.to(f32)])

@@ -285,6 +285,30 @@ int b200clip_adamw_g16(b200clip_ctx* ctx, float* master, void* param_bf16, const
                        int64_t n, float lr, float beta1, float beta2, float eps, float weight_decay, float grad_scale,
                        int64_t step, const float* hyper_dev, void* stream);
 
+/* ---- peer-memory all-gather over NVLink / NVSwitch (csrc/peer.cu) ---------------------------------
+ * Replaces the NCCL all-gather of the normalised features and of the row log-sum-exps that the data-parallel
+ * InfoNCE needs between the towers and the loss (the reference itself is single-GPU:
+ * CLIP/train.py:103).  One process per GPU; every rank owns a "symmetric" buffer that all peers map through
+ * CUDA IPC, and ONE kernel per rank publishes its block, raises a flag in every peer, waits for the peers'
+ * flags and pulls their blocks with loads through the NVLink fabric (protocol: csrc/peer.cu).
+ *   b200clip_peer_buffer_bytes  size of a symmetric buffer for `world` ranks and blocks of up to slot_bytes (-1: bad args)
+ *   b200clip_peer_alloc         cudaMalloc + zero + export: *ptr = device memory, handle64 = 64-byte IPC handle
+ *   b200clip_peer_open          map a peer's buffer from its handle (enables peer access lazily)
+ *   b200clip_peer_close / _free unmap a peer's buffer / free the own one
+ *   b200clip_peer_allgather     bufs_dev: DEVICE array [world] of the buffers as mapped in this process (own one at
+ *                               [rank]); 1..3 segments: dst[s] + r * bytes[s] <- rank r's src[s] (bytes[s] per rank,
+ *                               a multiple of 4; sum <= slot_bytes).  Every rank must make the same sequence of calls
+ *                               with the same sizes.  Stream-ordered, no host sync, CUDA-graph capturable.
+ *   b200clip_peer_status        out2[0] = calls completed, out2[1] = 1 if a wait ever timed out (4 s) */
+int64_t b200clip_peer_buffer_bytes(int world, int64_t slot_bytes);
+int b200clip_peer_alloc(b200clip_ctx* ctx, int64_t bytes, void** ptr, void* handle64);
+int b200clip_peer_open(b200clip_ctx* ctx, const void* handle64, void** ptr);
+int b200clip_peer_close(b200clip_ctx* ctx, void* ptr);
+int b200clip_peer_free(b200clip_ctx* ctx, void* ptr);
+int b200clip_peer_allgather(b200clip_ctx* ctx, const void* const* bufs_dev, int world, int rank, int64_t slot_bytes,
+                            int nseg, const void* const* src, void* const* dst, const int64_t* bytes, void* stream);
+int b200clip_peer_status(b200clip_ctx* ctx, const void* own_buf, int64_t* out2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,6 +26,48 @@ def main():
     from oracle import clip_oracle as O
     from construction_clip_b200.train import ClipTrainer, clip_contrastive_loss
 
+    # (0) the library's peer-memory all-gather (csrc/peer.cu) against NCCL's, eager and inside a replayed CUDA graph
+    from construction_clip_b200 import peer as P
+    ex = P.get(None, dev, 1 << 20)
+    peer_state = "off" if P.mode() != "peer" else ("unavailable" if ex is None else "on")
+    peer_ok = True
+    if ex is not None:
+        def nccl_gather(x):
+            out = torch.empty((world, x.numel()), device=dev, dtype=x.dtype)
+            dist.all_gather_into_tensor(out, x.contiguous())
+            return out
+        torch.manual_seed(1234 + rank)
+        for n in (3, 128, 128 * 512, 300001):
+            a, b = torch.randn(n, device=dev), torch.randn(2 * n, device=dev)
+            da, db = torch.empty((world, n), device=dev), torch.empty((world, 2 * n), device=dev)
+            ex.allgather([a, b], [da, db])
+            peer_ok &= torch.equal(da, nccl_gather(a)) and torch.equal(db, nccl_gather(b))
+        a = torch.randn(128 * 1024, device=dev)
+        c = torch.randn(128, device=dev)
+        da, dc = torch.empty((world, a.numel()), device=dev), torch.empty((world, c.numel()), device=dev)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            ex.allgather([a], [da])
+            ex.allgather([c], [dc])
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            ex.allgather([a], [da])
+            ex.allgather([c], [dc])
+        for i in range(5):   # odd number of calls per replay pair: both slots, both flag parities
+            a.normal_()
+            c.normal_()
+            da.zero_()
+            dc.zero_()
+            g.replay()
+            peer_ok &= torch.equal(da, nccl_gather(a)) and torch.equal(dc, nccl_gather(c))
+        peer_ok &= not ex.timed_out()
+        del g
+        if not peer_ok:
+            print(f"rank {rank}: peer all-gather mismatch", flush=True)
+
     name = os.environ.get("DIST_MODEL", "ViT-B/32")
     Bg = int(os.environ.get("DIST_BATCH", str(max(16, 8 * world))))
     cfg = O.CONFIGS[name]
@@ -56,7 +98,7 @@ def main():
     finally:
         T._world = real_world
     torch.cuda.synchronize()
-    ok = True
+    ok = peer_ok
     rel = abs(loss.item() - loss1.item()) / abs(loss1.item())
     if rel > 1e-3:
         ok = False
@@ -152,10 +194,13 @@ def main():
             if abs(a - b) > (1e-4 if i == 0 else 1e-2) * max(1.0, abs(a)):
                 ok = False
                 print(f"rank {rank}: graph/eager loss mismatch at step {i}: {a} vs {b}", flush=True)
+    if ex is not None and ex.timed_out():
+        ok = False
+        print(f"rank {rank}: a peer-exchange wait timed out", flush=True)
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"DIST_CHECK world={world} Bg={Bg} packed_text={T.T.PACK_TEXT and bl * 77 >= T.T.PACK_MIN_ROWS} "
+        print(f"DIST_CHECK world={world} Bg={Bg} peer_exchange={peer_state} packed_text={T.T.PACK_TEXT and bl * 77 >= T.T.PACK_MIN_ROWS} "
               f"oracle_loss_rel={orel:.2e} oracle_worst_grad_cos={ocos:.6f} "
               f"loss_sharded={loss.item():.6f} loss_single={loss1.item():.6f} rel={rel:.2e} "
               f"worst_grad_cos={worst:.6f} dls_rel={dls:.2e} autograd_cos={c2:.6f} replicas_identical={same} "

@@ -25,6 +25,9 @@ elif case.endswith("fc_dgrad"):
 elif case.endswith("proj_dgrad"):
     w = torch.randn(d, 4 * d, device=dev).to(bf16)
     fn = lambda: O.gemm(x, w, b_major=L.MAJOR_MN, epilogue=L.EPI_QUICKGELU_BWD, aux=x4)
+elif case.endswith("fc_wgrad"):
+    g = torch.zeros(4 * d, d, device=dev)
+    fn = lambda: O.gemm(x4, x, a_major=L.MAJOR_MN, b_major=L.MAJOR_MN, out=g, split_k=0, accumulate=True)
 elif case.endswith("qkv_fwd"):
     w = torch.randn(3 * d, d, device=dev).to(bf16); b = torch.randn(3 * d, device=dev).to(bf16)
     fn = lambda: O.gemm(x, w, bias=b)
