@@ -401,6 +401,18 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001 -- a secondary figure must never break the contract line
             variants["torch_eager_bf16"] = {"error": repr(exc)[:300]}
 
+    # which transport carried the features / log-sum-exps between the towers and the loss (N > 1)
+    from construction_clip_b200 import peer as PEER
+    feature_exchange = "none (one rank)"
+    if world > 1:
+        exs = [e for e in PEER._cache.values() if e is not None]
+        if exs:
+            if any(e.timed_out() for e in exs):
+                raise RuntimeError("peer exchange: a wait for a peer timed out; the measured step is invalid")
+            feature_exchange = "peer-memory all-gather over NVLink (csrc/peer.cu), one kernel per rank, in the step's graph"
+        else:
+            feature_exchange = f"NCCL ({PEER.mode()})"
+
     peaks = load_peaks()
     f_pair = 3.0 * ORC.flops_pair(ORC.CONFIGS[args.model])          # algorithmic FLOPs per trained pair
     step_tflops_per_gpu = value / world * f_pair / 1e12
@@ -430,6 +442,8 @@ def run_ours(args):
                 "caption_lengths": "U{3..76} tokens + EOT (SURVEY 8(d) synthetic recipe)",
                 "rows_executed_per_batch": text_rows, "rows_real_per_batch": real_rows, "rows_unpacked": bl * 77},
             "l2_policy": "inputs and per-step activations (>10 GB/step) exceed the 126 MB L2; no explicit flush",
+            "feature_exchange": feature_exchange,
+            "mlp_saved_for_backward": "uint8 code of QuickGELU'(c_fc(x))" if TW.QGELU_D8 else "bf16 pre-activation",
             "final_loss": final_loss,
             "algorithmic_gflop_per_pair": f_pair / 1e9,
             "step_tflops_per_gpu": step_tflops_per_gpu,

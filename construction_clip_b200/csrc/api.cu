@@ -83,6 +83,46 @@ int make_tmap_bf16_2d_sw(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, u
     return B200CLIP_OK;
 }
 
+int make_tmap_u8_2d_sw32(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1,
+                         uint64_t pitch_bytes, uint32_t box0, uint32_t box1) {
+    if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0 || pitch_bytes % 16 != 0 || box0 == 0 || box0 > 32 || box1 == 0 ||
+        box1 > 256) {
+        set_error("u8 tensor map: pointer %p / pitch %llu / box %u x %u", ptr, (unsigned long long)pitch_bytes, box0, box1);
+        return B200CLIP_ERR_ARG;
+    }
+    const uint64_t key[4] = {reinterpret_cast<uint64_t>(ptr), dim0, dim1,
+                             (pitch_bytes << 20) | (static_cast<uint64_t>(box0) << 10) | box1 | (1ull << 62)};
+    TmapCacheEntry* slot = nullptr;
+    if (ctx->tmap_cache != nullptr) {
+        uint64_t h = key[0] * 0x9E3779B97F4A7C15ull ^ key[1] * 0xC2B2AE3D27D4EB4Full ^ key[2] * 0x165667B19E3779F9ull ^ key[3];
+        h ^= h >> 29;
+        slot = &ctx->tmap_cache[h % kTmapCacheSize];
+        if (slot->key[0] == key[0] && slot->key[1] == key[1] && slot->key[2] == key[2] && slot->key[3] == key[3]) {
+            memcpy(out, &slot->map, sizeof(CUtensorMap));
+            ++ctx->tmap_hits;
+            return B200CLIP_OK;
+        }
+        ++ctx->tmap_misses;
+    }
+    cuuint64_t gdim[2] = {dim0, dim1};
+    cuuint64_t gstride[1] = {pitch_bytes};
+    cuuint32_t box[2] = {box0, box1};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = ctx->encode_tiled(out, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_32B,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled(u8) failed (%d): dims %llu x %llu pitch %llu box %u x %u", (int)r,
+                  (unsigned long long)dim0, (unsigned long long)dim1, (unsigned long long)pitch_bytes, box0, box1);
+        return B200CLIP_ERR_CUDA;
+    }
+    if (slot != nullptr) {
+        memcpy(&slot->map, out, sizeof(CUtensorMap));
+        memcpy(slot->key, key, sizeof(key));
+    }
+    return B200CLIP_OK;
+}
+
 int init_gemm(b200clip_ctx* ctx);
 int init_attention(b200clip_ctx* ctx);
 

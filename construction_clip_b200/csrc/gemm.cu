@@ -96,6 +96,7 @@ struct GemmParams {
     int split_k, kb_total, kb_per_split;
     int out_f32, atomic_out, epilogue;
     int tma_store;  // EPI_QUICKGELU only: row-layout epilogue, outputs leave through TMA stores (tmC / tmP are valid)
+    int d8;         // EPI_QUICKGELU: `preact` receives 8-bit codes of QuickGELU'(x) instead of x; EPI_QUICKGELU_BWD: `aux` holds them
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -146,6 +147,28 @@ __device__ __forceinline__ float qgelu_bwd_fast(float acc, float x) {
     return fmaf(h, c, h);
 }
 
+// QuickGELU'(x) = s + 1.702 x s (1 - s), s = sigmoid(1.702 x), lives in [-0.1008, 1.1008].  The backward needs nothing
+// else of the pre-activation, so the forward can save the derivative itself on an 8-bit grid instead of x in bf16:
+// code = round(210 g' + 22), g' = (code - 22) / 210 -- step 1 / 210 (0 and 1, the two tails, are exact grid points),
+// rms error 1.4e-3, evaluated from the fp32 pre-activation.  That is about what re-evaluating g' from a bf16-rounded
+// x costs (|g''| <= 0.85 times a relative 2^-9 of x), at half the bytes in both directions and without a MUFU in
+// the backward.  (B200CLIP_EPI_QUICKGELU_D8 / _BWD_D8.)
+constexpr float kD8Scale = 210.0f, kD8Zero = 22.0f;
+__device__ __forceinline__ uint32_t qgelu_fwd_d8(float x, float& g) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.4554669595930157f * x));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+    g = x * r;
+    const float gp = fmaf(1.702f * g, 1.0f - r, r);
+    // round to nearest through the magic-number add (1.5 * 2^23): the code lands in the low mantissa byte.  No F2I: the
+    // conversion unit is the one the ex2 / rcp above already keep busy.  g' is inside [-0.1008, 1.1008] by construction
+    // (the approximations are good to 1e-6), so 210 g' + 22 is inside [0.8, 253.2] and nothing has to saturate.
+    return __float_as_uint(fmaf(gp, kD8Scale, kD8Zero + 12582912.0f)) & 0xffu;
+}
+__device__ __forceinline__ float d8_decode(uint32_t word, int k) {   // byte k of a little-endian word of four codes
+    return fmaf(static_cast<float>((word >> (8 * k)) & 0xffu), 1.0f / kD8Scale, -kD8Zero / kD8Scale);
+}
+
 // per-lane aux operands of one 32x32 block (coalesced layout: 8 rows x 4 columns).  Fetched one block
 // ahead so that global-memory latency is off the critical path (the first block of a tile is fetched
 // before waiting for the MMA).  The bias of ALL the tile's blocks is fetched once per tile (drain_tile).
@@ -153,8 +176,10 @@ template <int EPI, bool OUT_F32>
 struct EpiOperands {
     static constexpr bool AUX_F32 = (EPI == B200CLIP_EPI_RESIDUAL) && OUT_F32;
     static constexpr bool AUX_BF16 = (EPI == B200CLIP_EPI_QUICKGELU_BWD) || (EPI == B200CLIP_EPI_RESIDUAL && !OUT_F32);
+    static constexpr bool AUX_U8 = (EPI == B200CLIP_EPI_QUICKGELU_BWD_D8);
     uint4 auxf[AUX_F32 ? 8 : 1];
     uint2 auxh[AUX_BF16 ? 8 : 1];
+    uint32_t auxb[AUX_U8 ? 8 : 1];
 
     // Loads are UNCONDITIONAL from clamped (always valid) addresses so that all eight are in flight
     // at once -- a `cond ? load : 0` select puts a dependent MOV behind every load and serialises
@@ -178,6 +203,14 @@ struct EpiOperands {
                     const int grow = min(m_base + 4 * i + rrow, p.M - 1);
                     auxf[i] = *reinterpret_cast<const uint4*>(ap + static_cast<int64_t>(grow) * p.ldaux);
                 }
+            }
+        }
+        if constexpr (AUX_U8) {
+            const uint8_t* ap = reinterpret_cast<const uint8_t*>(p.aux) + col;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int grow = FULL ? m_base + 4 * i + rrow : min(m_base + 4 * i + rrow, p.M - 1);
+                auxb[i] = *reinterpret_cast<const uint32_t*>(ap + static_cast<int64_t>(grow) * p.ldaux);
             }
         }
         if constexpr (AUX_BF16) {
@@ -211,7 +244,8 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
     using OutT = typename std::conditional<OUT_F32, float, __nv_bfloat16>::type;
     // column sums of C ride along in the QuickGELU' epilogue (c_fc bias gradient) and in the plain bf16
     // one (out_proj dgrad: the V third of in_proj_bias' gradient is the column sum of d(attention out))
-    constexpr bool kColsum = (EPI == B200CLIP_EPI_QUICKGELU_BWD) || (EPI == B200CLIP_EPI_NONE && !OUT_F32);
+    constexpr bool kColsum = (EPI == B200CLIP_EPI_QUICKGELU_BWD) || (EPI == B200CLIP_EPI_QUICKGELU_BWD_D8) ||
+                             (EPI == B200CLIP_EPI_NONE && !OUT_F32);
     const int rrow = lane >> 3, rch = lane & 7;
     const int col = col0 + rch * 4;
     const bool col_ok = FULL ? true : col < p.N;
@@ -280,6 +314,9 @@ __device__ __forceinline__ void epilogue_block(const GemmParams& p, const EpiOpe
                 if (ok) *reinterpret_cast<uint2*>(pptr) = make_uint2(pack_bf16(x0, x1), pack_bf16(x2, x3));
             }
             x0 = qgelu_fast(x0); x1 = qgelu_fast(x1); x2 = qgelu_fast(x2); x3 = qgelu_fast(x3);
+        } else if constexpr (Op::AUX_U8) {
+            x0 *= d8_decode(op.auxb[i], 0); x1 *= d8_decode(op.auxb[i], 1);
+            x2 *= d8_decode(op.auxb[i], 2); x3 *= d8_decode(op.auxb[i], 3);
         } else if constexpr (Op::AUX_F32) {
             x0 += __uint_as_float(op.auxf[i].x); x1 += __uint_as_float(op.auxf[i].y);
             x2 += __uint_as_float(op.auxf[i].z); x3 += __uint_as_float(op.auxf[i].w);
@@ -412,7 +449,9 @@ __device__ __forceinline__ void drain_tile(const GemmParams& p, uint64_t* full_b
 // 32 x 32 staging tile (conflict free: chunk ^ ((row >> 1) & 3)) and one lane hands the tile to the TMA unit, which
 // coalesces and clips it at the matrix edge: no transposition, no address arithmetic, no predicates, no LSU stores.
 // The bias of a block is the same 32 values for every lane: four warp-uniform 16-byte loads.
-template <bool PRE, bool PAIR>
+// D8 (with PRE): the second output is not the pre-activation but the 8-bit code of QuickGELU'(x) (32 bytes per row of a
+// block, 32-byte swizzle: chunk ^ ((row >> 2) & 1)).
+template <bool PRE, bool D8, bool PAIR>
 __device__ __forceinline__ void drain_tile_rows_qgelu(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmP,
                                                       uint64_t* full_bar, uint32_t phase, uint64_t* release_bar,
                                                       uint32_t taddr, int m_base, int n_base, int nblk, float scale,
@@ -447,17 +486,29 @@ __device__ __forceinline__ void drain_tile_rows_qgelu(const GemmParams& p, const
             }
         }
         uint32_t pg[16];
-        [[maybe_unused]] uint32_t pp[16];
+        [[maybe_unused]] uint32_t pp[D8 ? 8 : 16];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint32_t bw[4] = {bq[c].x, bq[c].y, bq[c].z, bq[c].w};
+            [[maybe_unused]] uint32_t codes[8];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float2 bf = unpack_bf16(bw[k]);
                 const float x0 = fmaf(__uint_as_float(acc[8 * c + 2 * k]), scale, bf.x);
                 const float x1 = fmaf(__uint_as_float(acc[8 * c + 2 * k + 1]), scale, bf.y);
-                if constexpr (PRE) pp[4 * c + k] = pack_bf16(x0, x1);
-                pg[4 * c + k] = pack_bf16(qgelu_fast(x0), qgelu_fast(x1));
+                if constexpr (PRE && D8) {
+                    float g0, g1;
+                    codes[2 * k] = qgelu_fwd_d8(x0, g0);
+                    codes[2 * k + 1] = qgelu_fwd_d8(x1, g1);
+                    pg[4 * c + k] = pack_bf16(g0, g1);
+                } else {
+                    if constexpr (PRE) pp[4 * c + k] = pack_bf16(x0, x1);
+                    pg[4 * c + k] = pack_bf16(qgelu_fast(x0), qgelu_fast(x1));
+                }
+            }
+            if constexpr (PRE && D8) {  // eight codes -> two little-endian words
+                pp[2 * c] = codes[0] | (codes[1] << 8) | (codes[2] << 16) | (codes[3] << 24);
+                pp[2 * c + 1] = codes[4] | (codes[5] << 8) | (codes[6] << 16) | (codes[7] << 24);
             }
         }
         // the previous block's stores must have read the staging tile before it is overwritten
@@ -467,8 +518,14 @@ __device__ __forceinline__ void drain_tile_rows_qgelu(const GemmParams& p, const
         for (int c = 0; c < 4; ++c) {
             const uint32_t off = (static_cast<uint32_t>(c) ^ sw) << 4;
             *reinterpret_cast<uint4*>(row_g + off) = make_uint4(pg[4 * c], pg[4 * c + 1], pg[4 * c + 2], pg[4 * c + 3]);
-            if constexpr (PRE)
+            if constexpr (PRE && !D8)
                 *reinterpret_cast<uint4*>(row_p + off) = make_uint4(pp[4 * c], pp[4 * c + 1], pp[4 * c + 2], pp[4 * c + 3]);
+        }
+        if constexpr (PRE && D8) {
+            uint8_t* row_d = stg + 2048 + lane * 32;
+            const uint32_t s32 = static_cast<uint32_t>((lane >> 2) & 1);
+            *reinterpret_cast<uint4*>(row_d + ((0u ^ s32) << 4)) = make_uint4(pp[0], pp[1], pp[2], pp[3]);
+            *reinterpret_cast<uint4*>(row_d + ((1u ^ s32) << 4)) = make_uint4(pp[4], pp[5], pp[6], pp[7]);
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -512,8 +569,8 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
     // ahead (plain prefetch.global.L2: -4 % on the two c_proj dgrad shapes).  Not for the fp32 residual
     // operand (measured +4 % there), and never with the bulk / TMA prefetch form (it queues behind the
     // mainloop's operand loads: up to 2.4x slower).
-    constexpr bool kHasAux = (EPI == B200CLIP_EPI_QUICKGELU_BWD);
-    constexpr int kAuxElem = (EPI == B200CLIP_EPI_RESIDUAL && OUT_F32) ? 4 : 2;
+    constexpr bool kHasAux = (EPI == B200CLIP_EPI_QUICKGELU_BWD) || (EPI == B200CLIP_EPI_QUICKGELU_BWD_D8);
+    constexpr int kAuxElem = (EPI == B200CLIP_EPI_RESIDUAL && OUT_F32) ? 4 : (EPI == B200CLIP_EPI_QUICKGELU_BWD_D8 ? 1 : 2);
     constexpr int kBlocks = BN / 32, kBase = kBlocks / kEpiParts, kRem = kBlocks % kEpiParts;
     constexpr int kBlocks0 = kBase + (kRem ? 1 : 0);                            // the largest share (<= 4)
     static_assert(kBlocks0 <= 4, "drain_tile handles at most four blocks per warp");
@@ -553,12 +610,15 @@ __device__ __forceinline__ void epilogue_loop(const GemmParams& p, uint32_t tmem
                                                       n_base, nblk, scale, stg, lane)
         if constexpr (EPI == B200CLIP_EPI_QUICKGELU) {
             if (p.tma_store) {  // kernel-uniform
-                if (p.preact != nullptr)
-                    drain_tile_rows_qgelu<true, PAIR>(p, tmC, tmP, &tmem_full_bar[as], aphase, &tmem_empty_bar[as], taddr,
-                                                      m_base, n_base, nblk, scale, stg, lane);
+                if (p.preact != nullptr && p.d8)
+                    drain_tile_rows_qgelu<true, true, PAIR>(p, tmC, tmP, &tmem_full_bar[as], aphase, &tmem_empty_bar[as],
+                                                            taddr, m_base, n_base, nblk, scale, stg, lane);
+                else if (p.preact != nullptr)
+                    drain_tile_rows_qgelu<true, false, PAIR>(p, tmC, tmP, &tmem_full_bar[as], aphase, &tmem_empty_bar[as],
+                                                             taddr, m_base, n_base, nblk, scale, stg, lane);
                 else
-                    drain_tile_rows_qgelu<false, PAIR>(p, tmC, tmP, &tmem_full_bar[as], aphase, &tmem_empty_bar[as], taddr,
-                                                       m_base, n_base, nblk, scale, stg, lane);
+                    drain_tile_rows_qgelu<false, false, PAIR>(p, tmC, tmP, &tmem_full_bar[as], aphase, &tmem_empty_bar[as],
+                                                              taddr, m_base, n_base, nblk, scale, stg, lane);
             } else if (p.preact != nullptr) {
                 if (full) B200_DRAIN(true, true);
                 else B200_DRAIN(false, true);
@@ -734,6 +794,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 case B200CLIP_EPI_QUICKGELU: EPI_LOOP_TMA(B200CLIP_EPI_QUICKGELU, false, false); break;
                 case B200CLIP_EPI_RESIDUAL: EPI_LOOP(B200CLIP_EPI_RESIDUAL, false, false); break;
                 case B200CLIP_EPI_QUICKGELU_BWD: EPI_LOOP(B200CLIP_EPI_QUICKGELU_BWD, false, false); break;
+                case B200CLIP_EPI_QUICKGELU_BWD_D8: EPI_LOOP(B200CLIP_EPI_QUICKGELU_BWD_D8, false, false); break;
                 default: EPI_LOOP(B200CLIP_EPI_NONE, false, false); break;
             }
         }
@@ -935,6 +996,7 @@ __device__ __forceinline__ void gemm_cluster_body(const CUtensorMap& tmA, const 
                 case B200CLIP_EPI_QUICKGELU: EPI_LOOP_TMA(B200CLIP_EPI_QUICKGELU, false, false); break;
                 case B200CLIP_EPI_RESIDUAL: EPI_LOOP(B200CLIP_EPI_RESIDUAL, false, false); break;
                 case B200CLIP_EPI_QUICKGELU_BWD: EPI_LOOP(B200CLIP_EPI_QUICKGELU_BWD, false, false); break;
+                case B200CLIP_EPI_QUICKGELU_BWD_D8: EPI_LOOP(B200CLIP_EPI_QUICKGELU_BWD_D8, false, false); break;
                 default: EPI_LOOP(B200CLIP_EPI_NONE, false, false); break;
             }
         }
@@ -990,7 +1052,9 @@ static int set_attr_quad() {
 static int make_store_tmaps(b200clip_ctx* ctx, const GemmParams& p, CUtensorMap* tmC, CUtensorMap* tmP) {
     if (!p.tma_store) return 0;
     int rc = make_tmap_bf16_2d_sw(ctx, tmC, p.C, p.N, p.M, p.ldc, 32, 32, 64);
-    if (rc == 0 && p.preact != nullptr) rc = make_tmap_bf16_2d_sw(ctx, tmP, p.preact, p.N, p.M, p.ldc, 32, 32, 64);
+    if (rc == 0 && p.preact != nullptr)
+        rc = p.d8 ? make_tmap_u8_2d_sw32(ctx, tmP, p.preact, p.N, p.M, p.ldc, 32, 32)   // 8-bit codes, same extents, pitch ldc BYTES
+                  : make_tmap_bf16_2d_sw(ctx, tmP, p.preact, p.N, p.M, p.ldc, 32, 32, 64);
     return rc;
 }
 
@@ -1181,7 +1245,14 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
     B200_CHECK_ARG(!(a_major == B200CLIP_MAJOR_MN && b_major == B200CLIP_MAJOR_K),
                    "gemm: (A MN-major, B K-major) is not instantiated");
     B200_CHECK_ARG(out_dtype == B200CLIP_DT_BF16 || out_dtype == B200CLIP_DT_F32, "gemm: bad out_dtype");
-    B200_CHECK_ARG(epilogue >= 0 && epilogue <= 3, "gemm: bad epilogue %d", epilogue);
+    B200_CHECK_ARG(epilogue >= 0 && epilogue <= 5, "gemm: bad epilogue %d", epilogue);
+    // the two 8-bit-derivative flavours: the forward is EPI_QUICKGELU whose second output is the code of QuickGELU'(x)
+    const bool fwd_d8 = epilogue == B200CLIP_EPI_QUICKGELU_D8;
+    if (fwd_d8) {
+        epilogue = B200CLIP_EPI_QUICKGELU;
+        B200_CHECK_ARG(preact != nullptr && out_dtype == B200CLIP_DT_BF16 && ldc % 16 == 0,
+                       "gemm: EPI_QUICKGELU_D8 needs the code output, a bf16 C and ldc %% 16 == 0");
+    }
     const bool out_f32 = out_dtype == B200CLIP_DT_F32;
     if (out_f32) {
         B200_CHECK_ARG(epilogue == B200CLIP_EPI_NONE || epilogue == B200CLIP_EPI_RESIDUAL,
@@ -1198,10 +1269,15 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
         B200_CHECK_ARG(ldaux % (out_f32 ? 4 : 8) == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0,
                        "gemm: aux not 16B aligned");
     }
+    if (epilogue == B200CLIP_EPI_QUICKGELU_BWD_D8) {
+        B200_CHECK_ARG(aux != nullptr && !out_f32, "gemm: EPI_QUICKGELU_BWD_D8 needs the 8-bit aux and a bf16 C");
+        B200_CHECK_ARG(ldaux % 16 == 0 && (reinterpret_cast<uintptr_t>(aux) & 15) == 0, "gemm: 8-bit aux not 16B aligned");
+    }
     B200_CHECK_ARG(bias == nullptr || (reinterpret_cast<uintptr_t>(bias) & 15) == 0, "gemm: bias not 16B aligned");
     B200_CHECK_ARG(preact == nullptr || (reinterpret_cast<uintptr_t>(preact) & 15) == 0, "gemm: preact misaligned");
     B200_CHECK_ARG(colsum == nullptr || ((reinterpret_cast<uintptr_t>(colsum) & 15) == 0 && !out_f32 &&
-                                         (epilogue == B200CLIP_EPI_QUICKGELU_BWD || epilogue == B200CLIP_EPI_NONE)),
+                                         (epilogue == B200CLIP_EPI_QUICKGELU_BWD || epilogue == B200CLIP_EPI_QUICKGELU_BWD_D8 ||
+                                          epilogue == B200CLIP_EPI_NONE)),
                    "gemm: colsum is fused into the bf16 EPI_NONE / EPI_QUICKGELU_BWD epilogues only, 16-byte aligned");
 
     GemmParams p{};
@@ -1225,7 +1301,8 @@ extern "C" int b200clip_gemm_bf16(b200clip_ctx* ctx, const void* A, int64_t lda,
         const char* e = getenv("B200CLIP_EPI_TMA");
         return !(e && atoi(e) == 0);
     }();
-    p.tma_store = (epi_tma && epilogue == B200CLIP_EPI_QUICKGELU && !out_f32) ? 1 : 0;
+    p.tma_store = ((epi_tma || fwd_d8) && epilogue == B200CLIP_EPI_QUICKGELU && !out_f32) ? 1 : 0;
+    p.d8 = fwd_d8 ? 1 : 0;
 
     // CTA-pair kernel (256 x 256 tiles over 74 clusters) when the problem has enough such tiles;
     // B200CLIP_GEMM_PAIR=0 disables it (tuning / bisecting)

@@ -102,6 +102,10 @@ int make_tmap_bf16_2d(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint
 int make_tmap_bf16_2d_sw(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1,
                          uint64_t pitch_elems, uint32_t box0, uint32_t box1, int swizzle_bytes);
 
+// 2-D uint8 tensor map, 32-byte swizzle, box0 <= 32 bytes (the 8-bit QuickGELU' codes of the c_fc forward epilogue)
+int make_tmap_u8_2d_sw32(b200clip_ctx* ctx, CUtensorMap* out, const void* ptr, uint64_t dim0, uint64_t dim1,
+                         uint64_t pitch_bytes, uint32_t box0, uint32_t box1);
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 }  // namespace b200

@@ -16,7 +16,7 @@ LIB_PATH = PKG / "libb200clip.so"
 
 # enums of include/b200clip.h
 MAJOR_K, MAJOR_MN = 0, 1
-EPI_NONE, EPI_QUICKGELU, EPI_RESIDUAL, EPI_QUICKGELU_BWD = 0, 1, 2, 3
+EPI_NONE, EPI_QUICKGELU, EPI_RESIDUAL, EPI_QUICKGELU_BWD, EPI_QUICKGELU_D8, EPI_QUICKGELU_BWD_D8 = 0, 1, 2, 3, 4, 5
 DT_BF16, DT_F32, DT_U8 = 0, 1, 2
 ABI_VERSION = 1
 

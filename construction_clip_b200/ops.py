@@ -62,8 +62,11 @@ def gemm(a, b, *, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, aux=None, pre
     if out is None:
         out = torch.empty((M, N), device=a.device, dtype=out_dtype)
     ldc = _row_major(out, "out")
-    if preact is not None:
-        assert _row_major(preact, "preact") == ldc and preact.dtype == bf16
+    if preact is not None:   # bf16 pre-activation, or the uint8 codes of QuickGELU' (EPI_QUICKGELU_D8: same extents, pitch in bytes)
+        assert _row_major(preact, "preact") == ldc
+        assert preact.dtype == (torch.uint8 if epilogue == L.EPI_QUICKGELU_D8 else bf16)
+    if epilogue == L.EPI_QUICKGELU_BWD_D8:
+        assert aux is not None and aux.dtype == torch.uint8
     ctx, st = _ctx_stream(a)
     prof = GEMM_PROFILE
     if prof is not None:
@@ -79,7 +82,7 @@ def gemm(a, b, *, a_major=L.MAJOR_K, b_major=L.MAJOR_K, bias=None, aux=None, pre
         e1.record()
         nbytes = (a.numel() + b.numel()) * 2 + out.numel() * out.element_size()
         nbytes += aux.numel() * aux.element_size() if aux is not None else 0
-        nbytes += preact.numel() * 2 if preact is not None else 0
+        nbytes += preact.numel() * preact.element_size() if preact is not None else 0
         prof.append((e0, e1, 2.0 * M * N * K, (a_major, b_major, M, N, K, nbytes)))
     return out
 

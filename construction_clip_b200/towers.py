@@ -39,6 +39,12 @@ POOL_LAST_BLOCK = os.environ.get("B200CLIP_POOL_LAST_BLOCK", "1") != "0"
 # every row-wise kernel and keep exactly-zero gradients.  Without a caller-supplied count (drop-in
 # `model(image, text)`), text_fwd reads it back from the device (one host sync) and only when the batch is
 # large enough for that to pay (PACK_MIN_ROWS).
+# What the MLP saves for its backward: the 8-bit code of QuickGELU'(c_fc(x)) instead of the bf16 pre-activation
+# (B200CLIP_EPI_QUICKGELU_D8 / _BWD_D8, csrc/gemm.cu).  The backward needs nothing else of the pre-activation; the code is
+# computed from the fp32 accumulator on a grid of 1/210 (rms error 1.4e-3 -- what re-evaluating the derivative from a
+# bf16-rounded pre-activation costs anyway), the c_fc forward writes 3 instead of 4 bytes per element and the c_proj
+# dgrad reads 1 instead of 2 and needs no MUFU.  B200CLIP_QGELU_D8=0 saves the pre-activation like round 1.
+QGELU_D8 = os.environ.get("B200CLIP_QGELU_D8", "1") != "0"
 PACK_TEXT = os.environ.get("B200CLIP_PACK_TEXT", "1") != "0"
 PACK_MIN_ROWS = int(os.environ.get("B200CLIP_PACK_MIN_ROWS", "4096"))
 
@@ -90,11 +96,12 @@ def _block_fwd(W, p, x, B, S, H, causal, save, cu=None):
                       out_dtype=f32)
     if save:
         h2, mean2, rstd2 = O.layernorm_fwd(x2, W[p + "ln_2.weight"], W[p + "ln_2.bias"], want_stats=True)
-        f = torch.empty((x.shape[0], 4 * x.shape[1]), device=x.device, dtype=bf16)
+        f = torch.empty((x.shape[0], 4 * x.shape[1]), device=x.device, dtype=torch.uint8 if QGELU_D8 else bf16)
     else:
         h2 = O.layernorm_fwd(x2, W[p + "ln_2.weight"], W[p + "ln_2.bias"])
         f = None
-    g = O.linear_fwd(h2, W[p + "mlp.c_fc.weight"], W[p + "mlp.c_fc.bias"], epilogue=L.EPI_QUICKGELU, preact=f)
+    g = O.linear_fwd(h2, W[p + "mlp.c_fc.weight"], W[p + "mlp.c_fc.bias"], preact=f,
+                     epilogue=L.EPI_QUICKGELU_D8 if (f is not None and QGELU_D8) else L.EPI_QUICKGELU)
     y = O.linear_fwd(g, W[p + "mlp.c_proj.weight"], W[p + "mlp.c_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x2,
                      out_dtype=f32)
     return y, (BlockSaved(x, mean1, rstd1, h1, qkv, a, lse, x2, mean2, rstd2, h2, f, g) if save else None)
@@ -145,11 +152,12 @@ def _last_block_fwd(W, p, x, B, S, H, causal, saved, pool_rows, cu=None):
                       out_dtype=f32)
     if save:
         h2, mean2, rstd2 = O.layernorm_fwd(x2, W[p + "ln_2.weight"], W[p + "ln_2.bias"], want_stats=True)
-        f = torch.empty((x2.shape[0], 4 * x2.shape[1]), device=x.device, dtype=bf16)
+        f = torch.empty((x2.shape[0], 4 * x2.shape[1]), device=x.device, dtype=torch.uint8 if QGELU_D8 else bf16)
     else:
         h2, mean2, rstd2 = O.layernorm_fwd(x2, W[p + "ln_2.weight"], W[p + "ln_2.bias"]), None, None
         f = None
-    g = O.linear_fwd(h2, W[p + "mlp.c_fc.weight"], W[p + "mlp.c_fc.bias"], epilogue=L.EPI_QUICKGELU, preact=f)
+    g = O.linear_fwd(h2, W[p + "mlp.c_fc.weight"], W[p + "mlp.c_fc.bias"], preact=f,
+                     epilogue=L.EPI_QUICKGELU_D8 if (f is not None and QGELU_D8) else L.EPI_QUICKGELU)
     y = O.linear_fwd(g, W[p + "mlp.c_proj.weight"], W[p + "mlp.c_proj.bias"], epilogue=L.EPI_RESIDUAL, aux=x2,
                      out_dtype=f32)
     if save:
@@ -188,7 +196,8 @@ def blocks_bwd(W, G, prefix, layers, dy, B, S, H, causal, saved: TowerSaved, on_
         dy_in = dy
         # ---- MLP branch: y = x2 + c_proj(gelu(c_fc(ln_2(x2))))
         wgrad(dy, s.g, G[p + "mlp.c_proj.weight"])
-        df = O.linear_dgrad(dy, W[p + "mlp.c_proj.weight"], epilogue=L.EPI_QUICKGELU_BWD, aux=s.f,
+        df = O.linear_dgrad(dy, W[p + "mlp.c_proj.weight"],
+                            epilogue=L.EPI_QUICKGELU_BWD_D8 if s.f.dtype == torch.uint8 else L.EPI_QUICKGELU_BWD, aux=s.f,
                             colsum=G[p + "mlp.c_fc.bias"])
         wgrad(df, s.h2, G[p + "mlp.c_fc.weight"])
         dh2 = O.linear_dgrad(df, W[p + "mlp.c_fc.weight"])

@@ -57,7 +57,12 @@ enum {
     B200CLIP_EPI_NONE = 0,          /* C = acc (+bias)                                      */
     B200CLIP_EPI_QUICKGELU = 1,     /* C = quickgelu(acc+bias); optional preact = acc+bias  */
     B200CLIP_EPI_RESIDUAL = 2,      /* C = acc + bias + aux  (aux has C's dtype: bf16 or f32) */
-    B200CLIP_EPI_QUICKGELU_BWD = 3  /* C = acc * quickgelu'(aux)                            */
+    B200CLIP_EPI_QUICKGELU_BWD = 3, /* C = acc * quickgelu'(aux)                            */
+    /* The same pair with the DERIVATIVE saved instead of the pre-activation: `preact` (forward) / `aux` (backward)
+     * is a uint8 [M,N] matrix (row pitch ldc / ldaux BYTES, a multiple of 16) of codes round(210 quickgelu'(x) + 22),
+     * computed from the fp32 pre-activation.  Half the bytes of the bf16 pre-activation in both directions. */
+    B200CLIP_EPI_QUICKGELU_D8 = 4,     /* C = quickgelu(acc+bias); preact (required) = code of quickgelu'(acc+bias) */
+    B200CLIP_EPI_QUICKGELU_BWD_D8 = 5  /* C = acc * (aux - 22) / 210                                                */
 };
 
 enum { B200CLIP_DT_BF16 = 0, B200CLIP_DT_F32 = 1, B200CLIP_DT_U8 = 2 /* im2col_patch input only */ };

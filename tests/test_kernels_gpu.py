@@ -151,6 +151,21 @@ def test_gemm_epilogues(ops, M, monkeypatch):
     cs = torch.zeros(N, device="cuda")
     _close(ops.gemm(a, w, epilogue=L.EPI_QUICKGELU_BWD, aux=aux, colsum=cs), gref, 3e-2, 1e-2, "quickgelu_bwd")
     _close(cs, gref.sum(0), 0.5, 1e-2, "fused colsum of C")
+    # the 8-bit-derivative pair: the forward saves round(210 quickgelu'(x) + 22), the backward multiplies by its decode
+    codes = torch.empty((M, N), device="cuda", dtype=torch.uint8)
+    got = ops.gemm(a, w, bias=bias, epilogue=L.EPI_QUICKGELU_D8, preact=codes)
+    _close(got, base * torch.sigmoid(1.702 * base), 3e-2, 1e-2, "quickgelu (d8)")
+    sb = torch.sigmoid(1.702 * base)
+    dref = sb * (1 + 1.702 * base * (1 - sb))
+    dgot = (codes.float() - 22.0) / 210.0
+    # half a grid step, plus the slope of the derivative times the bf16-level error of the accumulator
+    assert (dgot - dref).abs().max().item() <= 0.5 / 210 + 4e-3, (dgot - dref).abs().max().item()
+    assert (dgot - dref).abs().mean().item() <= 2e-3
+    cs8 = torch.zeros(N, device="cuda")
+    g8 = ops.gemm(a, w, epilogue=L.EPI_QUICKGELU_BWD_D8, aux=codes, colsum=cs8)
+    ref8 = (a.float() @ w.float().t()) * dgot
+    _close(g8, ref8, 3e-2, 1e-2, "quickgelu_bwd (d8)")
+    _close(cs8, ref8.sum(0), 0.5, 1e-2, "fused colsum of C (d8)")
     sc = torch.tensor([0.37], device="cuda")
     _close(ops.gemm(a, w, scale=sc, out_dtype=f32), 0.37 * (a.float() @ w.float().t()), 1e-3, 1e-3, "scale f32")
     # strided A (row pitch > K): the CLS-row gather pattern x[:, 0, :]

@@ -49,6 +49,11 @@ def tower(name, S, H, causal):
     cb = torch.zeros(4 * d, device=dev)
     cases.append((name + " proj_dgrad", lambda: O.gemm(dout, w_pr, b_major=L.MAJOR_MN, epilogue=L.EPI_QUICKGELU_BWD,
                                                        aux=pre, colsum=cb, out=dfc), 2 * M * 4 * d * d))
+    codes = torch.empty(M, 4 * d, device=dev, dtype=torch.uint8)
+    cases.append((name + " fc_fwd_d8", lambda: O.gemm(xb, w_fc, bias=b_fc, epilogue=L.EPI_QUICKGELU_D8, preact=codes, out=act),
+                  2 * M * 4 * d * d))
+    cases.append((name + " proj_dgrad_d8", lambda: O.gemm(dout, w_pr, b_major=L.MAJOR_MN, epilogue=L.EPI_QUICKGELU_BWD_D8,
+                                                          aux=codes, colsum=cb, out=dfc), 2 * M * 4 * d * d))
     w_o = torch.randn(d, d, device=dev).to(bf16) * 0.05
     b_o = torch.randn(d, device=dev).to(bf16)
     xo = torch.empty(M, d, device=dev)
