@@ -60,6 +60,7 @@ SIGNATURES = {
     "b200clip_check_im2col_f32": [_p, _p, _p, _l, _l, _l, _l, _p],
     "b200clip_adamw": [_p, _p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _l, _p, _p],
     "b200clip_adamw_g16": [_p, _p, _p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _f, _l, _p, _p],
+    "b200clip_resize_crop_u8": [_p, _p, _l, _l, _l, _p, _p, _l, _p, _p, _l, _l, _l, _p, _p, _l, _p],
     "b200clip_peer_buffer_bytes": [_i, _l],
     "b200clip_peer_alloc": [_p, _l, C.POINTER(_p), _p],
     "b200clip_peer_open": [_p, _p, C.POINTER(_p)],

@@ -280,6 +280,19 @@ def im2col_patch(image, patch, ldcols=None):
     return cols
 
 
+def resize_crop_u8(src, xbounds, xcoef, ybounds, ycoef, row0, rows, R):
+    """src uint8 [H, W, 3] (cuda) -> uint8 [3, R, R]: Pillow-exact bicubic resize + centre crop (tables from data.py)."""
+    assert src.dtype == torch.uint8 and src.dim() == 3 and src.shape[2] == 3 and src.stride(2) == 1 and src.stride(1) == 3
+    H, W, _ = src.shape
+    tmp = torch.empty((rows, R, 3), device=src.device, dtype=torch.uint8)
+    dst = torch.empty((3, R, R), device=src.device, dtype=torch.uint8)
+    ctx, st = _ctx_stream(src)
+    L.check(L.load().b200clip_resize_crop_u8(ctx, src.data_ptr(), H, W, src.stride(0), xbounds.data_ptr(), xcoef.data_ptr(),
+                                             xcoef.shape[1], ybounds.data_ptr(), ycoef.data_ptr(), ycoef.shape[1], row0,
+                                             rows, tmp.data_ptr(), dst.data_ptr(), R, st), "resize_crop_u8")
+    return dst
+
+
 def colsum(x, out):
     M, N = x.shape
     ctx, st = _ctx_stream(x)

@@ -200,6 +200,17 @@ int b200clip_scatter_rows(b200clip_ctx* ctx, const void* src, const int32_t* idx
 int b200clip_im2col_patch(b200clip_ctx* ctx, const void* image, int in_dtype, void* cols, int64_t ldcols, int64_t B,
                           int64_t R, int64_t patch, void* stream);
 
+/* ---- Resize(n_px, BICUBIC) + CenterCrop(n_px) of clip._transform on the GPU (CLIP/train.py:56, CLIP/predict.py:31) ----
+ * src: decoded RGB pixels, uint8 [H, W, 3] (row pitch src_pitch bytes) -> dst uint8 [3, R, R], bit-exact with Pillow's 8-bit
+ * resampler (two separable passes, 22-bit fixed-point coefficients).  The tables are built by the host
+ * (construction_clip_b200/data.py) for the R output columns / rows that survive the crop: xbounds / ybounds int32 [R, 2] =
+ * (first source index, tap count), xcoef / ycoef int32 [R, xk] / [R, yk].  The horizontal pass runs on source rows
+ * [row0, row0 + rows) -- the rows the vertical taps read -- into tmp uint8 [rows, R, 3] (caller-provided). */
+int b200clip_resize_crop_u8(b200clip_ctx* ctx, const void* src, int64_t H, int64_t W, int64_t src_pitch,
+                            const int32_t* xbounds, const int32_t* xcoef, int64_t xk, const int32_t* ybounds,
+                            const int32_t* ycoef, int64_t yk, int64_t row0, int64_t rows, void* tmp, void* dst, int64_t R,
+                            void* stream);
+
 /* ---- small fused helpers ---------------------------------------------------------------------- */
 /* colsum: out[n] (+)= sum_m x[m,n]; x bf16 [M,N] (ldx); out fp32 [N] accumulated (bias gradients). */
 int b200clip_colsum(b200clip_ctx* ctx, const void* x, int64_t ldx, float* out, int64_t M, int64_t N, void* stream);

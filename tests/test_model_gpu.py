@@ -709,3 +709,28 @@ def test_uint8_pixels_with_fused_normalize(name):
         b = m.encode_image(ref_in.cuda())
     assert cosine_rows(a.float().cpu(), ref).min() >= 0.999
     assert cosine_rows(a.float().cpu(), b.float().cpu()).min() >= 0.9999
+
+
+@pytest.mark.parametrize("h,w,n_px", [(480, 640, 224), (640, 427, 224), (224, 224, 224), (100, 150, 224), (237, 931, 336),
+                                      (1080, 1920, 224)])
+def test_gpu_preprocess_matches_pil(h, w, n_px):
+    """b200clip_resize_crop_u8 behind data.GpuPreprocess: Resize(BICUBIC) + CenterCrop of clip._transform on the GPU, bit
+    for bit what Pillow / torchvision produce on the host (the oracle restates them and is pinned against them in
+    tests/test_cpu.py); numpy, torch and PIL inputs."""
+    import numpy as np
+    from PIL import Image
+    from construction_clip_b200.data import GpuPreprocess
+    from oracle import resize_oracle as R
+    img = np.random.RandomState(h + w).randint(0, 256, (h, w, 3)).astype(np.uint8)
+    # a smooth image too: gradients exercise the rounding, noise the clipping
+    yy, xx = np.mgrid[0:h, 0:w]
+    smooth = np.stack([(xx * 255 // max(1, w - 1)), (yy * 255 // max(1, h - 1)), ((xx + yy) % 256)], -1).astype(np.uint8)
+    pre = GpuPreprocess(n_px, "cuda")
+    for im in (img, smooth):
+        ref = R.preprocess_uint8(im, n_px)
+        got = pre(im)
+        assert got.is_cuda and got.dtype == torch.uint8 and tuple(got.shape) == (3, n_px, n_px)
+        np.testing.assert_array_equal(got.cpu().numpy(), ref)
+        np.testing.assert_array_equal(pre(torch.from_numpy(im)).cpu().numpy(), ref)
+        np.testing.assert_array_equal(pre(Image.fromarray(im)).cpu().numpy(), ref)
+    assert tuple(pre.batch([img, smooth]).shape) == (2, 3, n_px, n_px)
