@@ -333,7 +333,9 @@ def run_ours(args):
     gemm_tflops = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     gemm_alg_bytes = sum(info[5] for _, _, _, info in gemm_prof) / max(1, len(gemm_prof))
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")   # ncu capture of the current step (tools/summarize_dram.py)
+    if not os.path.exists(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
     if world == 1 and os.path.exists(tpath):   # ncu capture of the same workload (N = 1), committed under profiles/
         with open(tpath) as fh:
             traffic = json.load(fh).get("dram_bytes_per_launch")
@@ -469,7 +471,7 @@ def run_ours(args):
         "roofline": {
             "bound": "tensor", "achieved": gemm_tflops, "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
             "frac": gemm_tflops / peaks["bf16_sustained"], "traffic": traffic,
-            "traffic_unit": "DRAM bytes per GEMM launch (ncu, profiles/r01_gemm_traffic.json)",
+            "traffic_unit": f"DRAM bytes per GEMM launch (ncu, profiles/{os.path.basename(tpath)})",
             "algorithmic_bytes_per_launch_avg": gemm_alg_bytes,
             "kernel": "gemm_bf16_kernel (tcgen05, all fwd/dgrad/wgrad launches)",
             "peak_source": f"{peaks['source']} (sustained cuBLAS bf16; kernel timed inside a long step)",
