@@ -407,7 +407,7 @@ def run_ours(args):
     from construction_clip_b200 import peer as PEER
     feature_exchange = "none (one rank)"
     if world > 1:
-        exs = [e for e in PEER._cache.values() if e is not None]
+        exs = PEER.active()
         if exs:
             if any(e.timed_out() for e in exs):
                 raise RuntimeError("peer exchange: a wait for a peer timed out; the measured step is invalid")

@@ -150,9 +150,14 @@ def mode() -> str:
     return os.environ.get("B200CLIP_FEATURE_GATHER", "peer")
 
 
+def active() -> list:
+    """The exchanges this process has set up (bench.py / tools check their time-out flags)."""
+    return [e for e in _cache.values() if e is not None]
+
+
 def get(group, device: torch.device, need_bytes: int):
     """The group's exchange if it exists (or can be created now) and holds `need_bytes` per rank; else None."""
-    if mode() != "peer":
+    if mode() != "peer" or device.type != "cuda" or not (dist.is_available() and dist.is_initialized()):
         return None
     key = (id(group) if group is not None else 0, device.index)
     if key not in _cache:
