@@ -693,6 +693,19 @@ def main():
                     help="BASELINE.json config: 2 (default) = the headline train step; 1/3/4/5 = secondary modes")
     args = ap.parse_args()
     _claim_stdout()
+    if args.impl != "reference" and int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # A multi-rank run normally ends within two minutes.  If a rank ever stalls in a collective, fail loudly instead of
+        # holding N GPUs until the launcher's own limit (BENCH_WATCHDOG_S=0 disables).
+        import threading
+        limit = float(os.environ.get("BENCH_WATCHDOG_S", "1200"))
+        if limit > 0:
+            def _abort():
+                sys.stderr.write(f"bench.py: no result after {limit:.0f} s on rank {os.environ.get('RANK')}; aborting\n")
+                sys.stderr.flush()
+                os._exit(3)
+            t = threading.Timer(limit, _abort)
+            t.daemon = True
+            t.start()
     if args.impl == "reference":
         run_reference(args)
     elif args.config != 2:
